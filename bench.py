@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — cell-updates/s of the fused diffusion+advection timestep on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W              # our CUDA path (default)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W   # one rank per GPU
+    python bench.py --impl reference ...                          # the reference's CPU code
+
+Workload (BASELINE.json configs[1]; per-GPU tile fixed as N grows → weak scaling): an 8192x8192
+tile per GPU, Gaussian hotspot, dx=dy=1, D=0.05, vx=0.5, vy=0, dt=0.1, all-periodic boundaries
+(= frozen zero ghosts), 2-D Cartesian decomposition {1,1},{2,1},{2,2},{4,2}.
+`--tile 16384` gives configs[2].
+
+A bench "step" is one output window of `--inner` (default 100, dev.yaml's out_every) time steps:
+  value : cells * inner * K / device time, fields resident in HBM, timed with CUDA events on the
+          library's stream, max over ranks.
+  e2e   : same window through the C ABI with HOST buffers: H2D of the padded tile from pinned
+          memory, `inner` steps, D2H of the de-haloed tile (what the reference hands to its NetCDF
+          writer at an output step), every step, inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PHYS = dict(D=0.05, vx=0.5, vy=0.0, dt=0.1)  # configs/dev.yaml physics
+ALG_BYTES_PER_CELL = 16.0                     # one 8-byte read + one 8-byte write per cell update
+METRIC = "cell updates/sec (diffusion+advection step)"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(2.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def workload_name(tile, dims):
+    return (f"{tile}x{tile} per GPU, Gaussian hotspot, diffusion+advection, periodic BCs, "
+            f"decomp {{{dims[0]},{dims[1]}}} (global {tile * dims[0]}x{tile * dims[1]})")
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_rate(tile, timesteps, threads):
+    """The reference's own compute objects (oracle/_ref) on `threads` emulated ranks: returns
+    (cell-updates/s, loop seconds, kind).  Falls back to the C port if _ref is absent."""
+    from oracle import cpu_oracle as co
+    if not co.available("port"):
+        co.build()
+    kind = "reference" if co.available("ref") else "port"
+    orc = co.Oracle("ref" if kind == "reference" else "port")
+    p = co.SimParams(nx=tile, ny=tile, steps=timesteps, out_every=10 ** 9, bc=(2, 2, 2, 2), **PHYS)
+    if kind == "reference":
+        r = orc.run(p, nranks=threads, want_frames=False, want_final=False)
+        secs = r["seconds"]
+    else:
+        threads = 1
+        t0 = time.perf_counter()
+        orc.run(p, nranks=1, want_frames=False, want_final=False)
+        secs = time.perf_counter() - t0
+    return tile * tile * timesteps / secs, secs, kind, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # rank emulation wants a count the decomposition likes; cap at 64 threads
+    threads = min(threads, 64)
+    inner = args.ref_inner
+    tile = args.tile
+    rates, secs = [], []
+    for i in range(args.warmup + args.steps):
+        rate, s, kind, used = cpu_reference_rate(tile, inner, threads)
+        if i >= args.warmup:
+            rates.append(rate)
+            secs.append(s)
+    total_cells = tile * tile * inner * len(secs)
+    value = total_cells / sum(secs)
+    sample = (f"{tile}x{tile} single tile split over {used} emulated ranks (threads), {inner} time steps per "
+              f"bench step, loop time only (main.cpp:89-123 timing region without NetCDF writes); "
+              f"reference compute objects, -O2, no MPI launcher (MPI not installed)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(tile, (1, 1)), "timesteps_per_step": inner},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    csim = importlib.import_module("climate-sim-mpi-cpp_b200")
+    ctx = csim.Context(local_rank)
+    tile, inner = args.tile, args.inner
+    dims = csim.Decomp2D.init(world, 0, 1, 1).dims
+    nxg, nyg = tile * dims[0], tile * dims[1]
+    dec = csim.Decomp2D.init(world, rank, nxg, nyg)
+    if world > 1:
+        box = [csim.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(world, rank, box[0])
+
+    P = csim.BCType.Periodic
+    params = csim.make_step_params(PHYS["D"], PHYS["vx"], PHYS["vy"], PHYS["dt"], csim.BCConfig(P, P, P, P), dec)
+    host_in = ctx.pinned_empty((dec.ny_local + 2, dec.nx_local + 2))
+    host_in[:] = 0.0
+    csim.initial_condition_host(dec, 1, 1.0, 1.0, out=host_in)
+    host_out = ctx.pinned_empty((dec.ny_local, dec.nx_local))
+    u = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
+    tmp = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
+    u.upload(host_in)
+
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count - l0
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            launches = int(lt.item())
+        return ms, launches
+
+    def window_resident():
+        csim.run_steps(u, tmp, params, dec, inner)
+
+    def window_e2e():
+        u.upload_async(host_in)
+        csim.run_steps(u, tmp, params, dec, inner)
+        u.download_interior_async(host_out)
+        ctx.sync()  # the caller needs the frame on the host before the next window
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(window_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(window_e2e, max(2, min(args.steps, 3)), 1)
+    e2e_steps = max(2, min(args.steps, 3))
+
+    cells_per_window = float(nxg) * float(nyg) * inner
+    value = cells_per_window * args.steps / (ms * 1e-3)
+    e2e_value = cells_per_window * e2e_steps / (ms_e2e * 1e-3)
+
+    # sanity: the field must still be finite and must have moved (the work was really done)
+    max_abs, bad = u.health()
+    if bad or not (0.0 < max_abs <= 1.0):
+        raise SystemExit(f"bench.py: field unhealthy after timing (max|u|={max_abs}, nonfinite={bad})")
+
+    # roofline of the dominant kernel: the fused step sweep, one launch per time step per GPU.
+    # With all-periodic boundaries no boundary kernels run, so the timed region on one GPU is
+    # exactly K*inner launches of it; with N>1 the exchange kernels share the region.
+    peak, peak_src = measured_peak_gbs()
+    step_launches = args.steps * inner
+    launch_ms = ms / step_launches
+    bytes_per_launch = float(dec.nx_local) * float(dec.ny_local) * ALG_BYTES_PER_CELL
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(str(tile), {}).get("bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "fused step sweep (csim::k_step_*)", "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": launch_ms,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = min(os.cpu_count() or 1, 64)
+        ref_steps = args.ref_inner * 3
+        rate, secs, kind, used = cpu_reference_rate(tile, ref_steps, threads)
+        cpu = {"value": rate, "unit": "cell-updates/s", "cores": used, "kind": kind,
+               "sample": f"{tile}x{tile}, {ref_steps} time steps of the same workload on {used} emulated ranks "
+                         f"(threads), {secs:.1f} s loop time; reference compute objects -O2, no MPI launcher"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(tile, dims), "timesteps_per_step": inner,
+                       "parallelism": f"cartesian {dims[0]}x{dims[1]}, 1 rank per GPU",
+                       "l2_policy": "inputs larger than L2 (two 537 MB fields per GPU vs 126 MB L2); no flush needed"
+                       if tile >= 4096 else "WARNING: fields fit in L2"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    u.close()
+    tmp.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--tile", type=int, default=8192, help="per-GPU tile edge (8192 = configs[1], 16384 = configs[2])")
+    ap.add_argument("--inner", type=int, default=100, help="time steps per bench step (output window)")
+    ap.add_argument("--ref-inner", type=int, default=4, help="time steps per bench step for the CPU reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print(f"bench.py: note: warmup {args.warmup} < 3", file=sys.stderr)
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
+
+
+if __name__ == "__main__":
+    main()

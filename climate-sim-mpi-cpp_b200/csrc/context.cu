@@ -1,0 +1,266 @@
+// context.cu — contexts, device tiles and host<->device movement of libcsim_b200.so.
+//
+// Stands behind the reference's Field (include/field.hpp:5-21, src/field.cpp:6-31): a Field
+// becomes a halo-padded, pitch-aligned device allocation (csim_field); the host keeps the
+// reference layout and these calls convert between the two with pitched 2-D copies.
+#include <cmath>
+#include <cstring>
+
+#include "csim_internal.hpp"
+
+namespace csim {
+
+static thread_local std::string t_last_error;
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    t_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", static_cast<int>(e),
+                  cudaGetErrorString(e), file, line, what);
+    t_last_error = buf;
+    return e == cudaErrorMemoryAllocation ? CSIM_ERR_NOMEM : CSIM_ERR_CUDA;
+}
+bool is_pow2(double x) {
+    if (!(x > 0.0) || !std::isfinite(x)) return false;
+    int e = 0;
+    const double m = std::frexp(x, &e);
+    // keep both x and 1/x normal so the reciprocal is exact
+    return m == 0.5 && e > -1000 && e < 1000;
+}
+
+__global__ void k_fill(double* __restrict__ p, int64_t n, double v) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride)
+        p[k] = v;
+}
+
+}  // namespace csim
+
+using namespace csim;
+
+extern "C" {
+
+const char* csim_last_error(void) { return t_last_error.c_str(); }
+int csim_abi_version(void) { return CSIM_ABI_VERSION; }
+
+int csim_ctx_create(int device, csim_ctx** out) {
+    CSIM_REQUIRE(out != nullptr, CSIM_ERR_INVALID, "csim_ctx_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CSIM_ERR_CUDA,
+                    std::string("csim_ctx_create: no CUDA device (this library has no CPU path): ") +
+                        cudaGetErrorString(e));
+    CSIM_REQUIRE(device >= 0 && device < ndev, CSIM_ERR_INVALID, "csim_ctx_create: bad device index");
+    CSIM_CUDA(cudaSetDevice(device));
+    csim_ctx* c = new (std::nothrow) csim_ctx();
+    CSIM_REQUIRE(c != nullptr, CSIM_ERR_NOMEM, "csim_ctx_create: host allocation failed");
+    c->device = device;
+    cudaDeviceProp prop;
+    CSIM_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CSIM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->scratch_doubles = 4096;
+    CSIM_CUDA(cudaMalloc(&c->d_scratch, c->scratch_doubles * sizeof(double)));
+    CSIM_CUDA(cudaMallocHost(&c->h_scratch, c->scratch_doubles * sizeof(double)));
+    *out = c;
+    return CSIM_OK;
+}
+
+int csim_ctx_destroy(csim_ctx* c) {
+    if (!c) return CSIM_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) csim_comm_destroy(c);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->d_pack) cudaFree(c->d_pack);
+    delete c;
+    return CSIM_OK;
+}
+
+int csim_sync(csim_ctx* c) {
+    CSIM_REQUIRE(c != nullptr, CSIM_ERR_INVALID, "csim_sync: ctx is null");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    return CSIM_OK;
+}
+
+void* csim_ctx_stream(csim_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+int csim_ctx_device(const csim_ctx* c) { return c ? c->device : -1; }
+uint64_t csim_ctx_launch_count(const csim_ctx* c) { return c ? c->launches : 0; }
+
+int csim_field_create(csim_ctx* c, int nx, int ny, int halo, double dx, double dy,
+                      csim_field** out) {
+    CSIM_REQUIRE(c != nullptr && out != nullptr, CSIM_ERR_INVALID, "csim_field_create: null argument");
+    *out = nullptr;
+    CSIM_REQUIRE(nx >= 0 && ny >= 0, CSIM_ERR_INVALID, "csim_field_create: negative size");
+    CSIM_REQUIRE(halo >= 0 && halo <= kMaxHalo, CSIM_ERR_UNSUPPORTED,
+                 "csim_field_create: halo must be in [0, 8]");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    csim_field* f = new (std::nothrow) csim_field();
+    CSIM_REQUIRE(f != nullptr, CSIM_ERR_NOMEM, "csim_field_create: host allocation failed");
+    f->ctx = c;
+    f->nx = nx;
+    f->ny = ny;
+    f->h = halo;
+    f->dx = dx;
+    f->dy = dy;
+    f->pitch = (static_cast<int64_t>(kLeadX) + nx + kTailX + 15) / 16 * 16;
+    f->rows = static_cast<int64_t>(ny) + 2 * kLeadY;
+    const size_t bytes = static_cast<size_t>(f->pitch) * static_cast<size_t>(f->rows) * sizeof(double);
+    cudaError_t e = cudaMalloc(&f->base, bytes);
+    if (e != cudaSuccess) {
+        delete f;
+        return cuda_fail(e, "cudaMalloc(field)", __FILE__, __LINE__);
+    }
+    // std::vector<double>(n, 0.0) — src/field.cpp:12
+    e = cudaMemsetAsync(f->base, 0, bytes, c->stream);
+    if (e != cudaSuccess) {
+        cudaFree(f->base);
+        delete f;
+        return cuda_fail(e, "cudaMemsetAsync(field)", __FILE__, __LINE__);
+    }
+    *out = f;
+    return CSIM_OK;
+}
+
+int csim_field_destroy(csim_field* f) {
+    if (!f) return CSIM_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    if (f->base) cudaFree(f->base);
+    delete f;
+    return CSIM_OK;
+}
+
+int csim_field_get_info(const csim_field* f, csim_field_info* o) {
+    CSIM_REQUIRE(f != nullptr && o != nullptr, CSIM_ERR_INVALID, "csim_field_get_info: null argument");
+    o->nx = f->nx;
+    o->ny = f->ny;
+    o->halo = f->h;
+    o->dx = f->dx;
+    o->dy = f->dy;
+    o->pitch = f->pitch;
+    o->lead_x = kLeadX;
+    o->lead_y = kLeadY;
+    o->rows = f->rows;
+    o->base = f->base;
+    o->interior = f->interior();
+    return CSIM_OK;
+}
+
+int csim_field_fill(csim_field* f, double value) {
+    CSIM_REQUIRE(f != nullptr, CSIM_ERR_INVALID, "csim_field_fill: field is null");
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    // Field::fill covers the padded tile (src/field.cpp:31); filling the whole allocation is a
+    // superset and keeps the wide-halo padding defined.
+    const int64_t n = f->pitch * f->rows;
+    CSIM_LAUNCH(c, k_fill, c->sm_count * 8, 256, 0, f->base, n, value);
+    return CSIM_OK;
+}
+
+static int copy2d(const csim_field* f, void* dst, size_t dpitch, const void* src, size_t spitch,
+                  size_t width_doubles, size_t height, cudaMemcpyKind kind, bool sync) {
+    if (width_doubles == 0 || height == 0) return CSIM_OK;
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    CSIM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_doubles * sizeof(double), height, kind,
+                                c->stream));
+    if (sync) CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    return CSIM_OK;
+}
+
+int csim_field_upload(csim_field* f, const double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload: null argument");
+    return copy2d(f, f->at(0, 0), f->pitch * sizeof(double), host, f->nxt() * sizeof(double), f->nxt(),
+                  f->nyt(), cudaMemcpyHostToDevice, true);
+}
+int csim_field_upload_async(csim_field* f, const double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload_async: null argument");
+    return copy2d(f, f->at(0, 0), f->pitch * sizeof(double), host, f->nxt() * sizeof(double), f->nxt(),
+                  f->nyt(), cudaMemcpyHostToDevice, false);
+}
+int csim_field_download(const csim_field* f, double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_download: null argument");
+    return copy2d(f, host, f->nxt() * sizeof(double), f->at(0, 0), f->pitch * sizeof(double), f->nxt(),
+                  f->nyt(), cudaMemcpyDeviceToHost, true);
+}
+int csim_field_download_interior(const csim_field* f, double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID,
+                 "csim_field_download_interior: null argument");
+    return copy2d(f, host, f->nx * sizeof(double), f->interior(), f->pitch * sizeof(double), f->nx, f->ny,
+                  cudaMemcpyDeviceToHost, true);
+}
+int csim_field_download_interior_async(const csim_field* f, double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID,
+                 "csim_field_download_interior_async: null argument");
+    return copy2d(f, host, f->nx * sizeof(double), f->interior(), f->pitch * sizeof(double), f->nx, f->ny,
+                  cudaMemcpyDeviceToHost, false);
+}
+
+// check_bounds of src/field.cpp:14-18
+static bool in_bounds(const csim_field* f, int i, int j) {
+    return !(i < 0 || j < 0 || i >= f->nxt() || j >= f->nyt());
+}
+int csim_field_get(const csim_field* f, int i, int j, double* value) {
+    CSIM_REQUIRE(f != nullptr && value != nullptr, CSIM_ERR_INVALID, "csim_field_get: null argument");
+    CSIM_REQUIRE(in_bounds(f, i, j), CSIM_ERR_RANGE, "Field index out of range");
+    CSIM_CUDA(cudaSetDevice(f->ctx->device));
+    CSIM_CUDA(cudaMemcpyAsync(value, f->at(i, j), sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CSIM_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CSIM_OK;
+}
+int csim_field_set(csim_field* f, int i, int j, double value) {
+    CSIM_REQUIRE(f != nullptr, CSIM_ERR_INVALID, "csim_field_set: field is null");
+    CSIM_REQUIRE(in_bounds(f, i, j), CSIM_ERR_RANGE, "Field index out of range");
+    CSIM_CUDA(cudaSetDevice(f->ctx->device));
+    CSIM_CUDA(cudaMemcpyAsync(f->at(i, j), &value, sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+    CSIM_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return CSIM_OK;
+}
+
+static bool same_geometry(const csim_field* a, const csim_field* b) {
+    return a->ctx == b->ctx && a->nx == b->nx && a->ny == b->ny && a->h == b->h && a->pitch == b->pitch &&
+           a->rows == b->rows;
+}
+
+int csim_field_swap(csim_field* a, csim_field* b) {
+    CSIM_REQUIRE(a != nullptr && b != nullptr, CSIM_ERR_INVALID, "csim_field_swap: null argument");
+    CSIM_REQUIRE(same_geometry(a, b), CSIM_ERR_INVALID, "csim_field_swap: tiles differ in geometry");
+    double* t = a->base;
+    a->base = b->base;
+    b->base = t;
+    return CSIM_OK;
+}
+
+int csim_field_copy(const csim_field* src, csim_field* dst) {
+    CSIM_REQUIRE(src != nullptr && dst != nullptr, CSIM_ERR_INVALID, "csim_field_copy: null argument");
+    CSIM_REQUIRE(same_geometry(src, dst), CSIM_ERR_INVALID, "csim_field_copy: tiles differ in geometry");
+    CSIM_CUDA(cudaSetDevice(src->ctx->device));
+    CSIM_CUDA(cudaMemcpyAsync(dst->base, src->base,
+                              static_cast<size_t>(src->pitch) * src->rows * sizeof(double),
+                              cudaMemcpyDeviceToDevice, src->ctx->stream));
+    return CSIM_OK;
+}
+
+int csim_host_alloc(size_t bytes, void** out) {
+    CSIM_REQUIRE(out != nullptr, CSIM_ERR_INVALID, "csim_host_alloc: out is null");
+    CSIM_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return CSIM_OK;
+}
+int csim_host_free(void* p) {
+    if (p) CSIM_CUDA(cudaFreeHost(p));
+    return CSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// csim_internal.hpp — private declarations shared by the translation units of libcsim_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "csim.h"
+
+// Device tile geometry (DESIGN.md "data layout in HBM").  A row holds kLeadX doubles of padding,
+// then the interior; the interior origin of every row is 128-byte aligned, the pitch is a multiple
+// of 128 bytes, and kLeadY rows precede interior row 0.  Ghost cells of a Field with halo h live at
+// x in [-h,0) and [nx,nx+h), i.e. inside the padding; the extra padding is what the wide-halo
+// (temporally blocked, multi-GPU) path uses.
+constexpr int kLeadX = 16;
+constexpr int kTailX = 16;
+constexpr int kLeadY = 8;
+constexpr int kMaxHalo = 8;
+
+struct csim_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // scratch for reductions: device partials + pinned host landing zone
+    double* d_scratch = nullptr;
+    double* h_scratch = nullptr;
+    size_t scratch_doubles = 0;
+    // NCCL state (halo.cu)
+    void* comm = nullptr;
+    int comm_size = 1, comm_rank = 0;
+    double* d_pack = nullptr;  // 4 column buffers: send L, send R, recv L, recv R
+    size_t pack_doubles = 0;
+    int sm_count = 148;
+};
+
+struct csim_field {
+    csim_ctx* ctx = nullptr;
+    int nx = 0, ny = 0, h = 0;
+    double dx = 1.0, dy = 1.0;
+    int64_t pitch = 0, rows = 0;
+    double* base = nullptr;
+    double* interior() const { return base + static_cast<int64_t>(kLeadY) * pitch + kLeadX; }
+    int nxt() const { return nx + 2 * h; }
+    int nyt() const { return ny + 2 * h; }
+    // pointer to padded-coordinate cell (i,j) = Field::at(i,j)
+    double* at(int i, int j) const { return interior() + static_cast<int64_t>(j - h) * pitch + (i - h); }
+};
+
+namespace csim {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// 1/x is exact and x*(1/x)==1 iff x is a (normal) power of two
+bool is_pow2(double x);
+
+}  // namespace csim
+
+#define CSIM_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return csim::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define CSIM_REQUIRE(cond, code, msg)                 \
+    do {                                              \
+        if (!(cond)) return csim::fail((code), (msg)); \
+    } while (0)
+
+// launch bookkeeping: every kernel launch of the library goes through this
+#define CSIM_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        ++(ctx)->launches;                                                       \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) return csim::cuda_fail(e__, #kernel, __FILE__, __LINE__); \
+    } while (0)

@@ -1,0 +1,431 @@
+// kernels.cu — the device kernels of the timestep path and their C-ABI launchers.
+//
+// Arithmetic contract (bit parity with the reference CPU build): every FP64
+// operation is issued through __dadd_rn/__dsub_rn/__dmul_rn/__ddiv_rn, which round to nearest-even
+// and are never contracted into FMA, in exactly the reference's order:
+//   lap  = ((e - 2.0*c) + w) / (dx*dx) + ((n - 2.0*c) + s) / (dy*dy)      src/diffusion.cpp:12-13
+//   o    = c + (dt*D) * lap                                               src/diffusion.cpp:14
+//   dudx = vx>=0 ? (c - w)/dx : (e - c)/dx                                src/advection.cpp:16-20
+//   dudy = vy>=0 ? (c - s)/dy : (n - c)/dy                                src/advection.cpp:23-27
+//   o    = o + (-dt) * (vx*dudx + vy*dudy)                                src/advection.cpp:29-31
+// Division by a power of two is replaced by multiplication with its exact reciprocal (same real
+// value, same rounding); any other spacing keeps IEEE division unless CSIM_STEP_FAST_RECIP is set.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "csim_internal.hpp"
+#include "step_math.cuh"
+
+namespace csim {
+
+// ---- reference-shaped single-function kernels (API parity, not the hot path) ------------------
+
+// diffusion_step interior, src/diffusion.cpp:9-16.  One thread per cell; u/out are interior
+// pointers (cell (0,0) = Field::at(h,h)).
+template <bool kDiv>
+__global__ void __launch_bounds__(256) k_diffusion(const double* __restrict__ u, double* __restrict__ out,
+                                                   int nx, int ny, int64_t pitch, StepK k) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const double* p = u + static_cast<int64_t>(y) * pitch + x;
+    const double c = p[0];
+    out[static_cast<int64_t>(y) * pitch + x] = diffusion_update<kDiv>(c, p[-1], p[1], p[-pitch], p[pitch], k);
+}
+
+// advection_step, src/advection.cpp:13-33: out += (-dt)*adv
+template <bool kDiv>
+__global__ void __launch_bounds__(256) k_advection(const double* __restrict__ u, double* __restrict__ out,
+                                                   int nx, int ny, int64_t pitch, StepK k) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const double* p = u + static_cast<int64_t>(y) * pitch + x;
+    const double c = p[0];
+    double* q = out + static_cast<int64_t>(y) * pitch + x;
+    *q = __dadd_rn(*q, advection_increment<kDiv>(c, p[-1], p[1], p[-pitch], p[pitch], k));
+}
+
+// Outermost ring of out := that of u, src/diffusion.cpp:18-25.  Pointers address padded cell
+// (0,0); nxt/nyt are the padded sizes.
+__global__ void k_ring_copy(const double* __restrict__ u, double* __restrict__ out, int nxt, int nyt,
+                            int64_t pitch) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nxt) {
+        out[t] = u[t];
+        out[static_cast<int64_t>(nyt - 1) * pitch + t] = u[static_cast<int64_t>(nyt - 1) * pitch + t];
+    }
+    if (t < nyt) {
+        out[static_cast<int64_t>(t) * pitch] = u[static_cast<int64_t>(t) * pitch];
+        out[static_cast<int64_t>(t) * pitch + nxt - 1] = u[static_cast<int64_t>(t) * pitch + nxt - 1];
+    }
+}
+
+// apply_boundary, left and right columns: src/boundary.cpp:23-37.  f addresses padded cell (0,0).
+// mode: -1 skip (side has a neighbour, or Periodic), 0 Dirichlet, 1 Neumann.
+__global__ void k_bc_columns(double* __restrict__ f, int nx, int ny, int h, int64_t pitch, int mode_l,
+                             int mode_r, double value) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > h + ny) return;  // rows jB..jT = 0..h+ny
+    double* row = f + static_cast<int64_t>(j) * pitch;
+    if (mode_l == 0)
+        row[0] = value;
+    else if (mode_l == 1)
+        row[0] = row[h];
+    if (mode_r == 0)
+        row[h + nx] = value;
+    else if (mode_r == 1)
+        row[h + nx] = row[h + nx - 1];
+}
+// bottom and top rows: src/boundary.cpp:39-53 (runs after the columns, so corners end up with the
+// row rule and Neumann rows read the freshly written column ghosts, as in the reference).
+__global__ void k_bc_rows(double* __restrict__ f, int nx, int ny, int h, int64_t pitch, int mode_b,
+                          int mode_t, double value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx + 2 * h) return;  // i0..i1 = 0..nx_tot-1
+    if (mode_b == 0)
+        f[i] = value;
+    else if (mode_b == 1)
+        f[i] = f[static_cast<int64_t>(h) * pitch + i];
+    double* top = f + static_cast<int64_t>(h + ny) * pitch;
+    if (mode_t == 0)
+        top[i] = value;
+    else if (mode_t == 1)
+        top[i] = f[static_cast<int64_t>(h + ny - 1) * pitch + i];
+}
+
+// ---- fused step, version 1: one sweep, one step ------------------------------------------------
+// Each thread owns two x-adjacent cells (one 16-byte load) and walks kRowsV1 rows with the
+// south/centre/north rows in registers, so every interior cell is loaded from HBM once; the two
+// x-neighbours outside the pair are scalar loads that hit L1 (the adjacent thread's line).
+// Writes the interior of `out` and the ghost ring of `out` := ghost ring of `u` (diffusion.cpp:18-25),
+// which replaces the reference's std::copy(u → tmp) (main.cpp:104).
+constexpr int kRowsV1 = 16;
+
+template <bool kDiv>
+__global__ void __launch_bounds__(256) k_step_v1(const double* __restrict__ u, double* __restrict__ out,
+                                                 int nx, int ny, int64_t pitch, StepK k) {
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 2;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kRowsV1;
+    if (x >= nx || y0 >= ny) return;
+    const int y1 = min(y0 + kRowsV1, ny);
+    const bool has2 = x + 1 < nx;
+
+    const double* p = u + static_cast<int64_t>(y0 - 1) * pitch + x;
+    double2 s = *reinterpret_cast<const double2*>(p);
+    if (y0 == 0 && x == 0) out[-pitch - 1] = p[-1];  // corner (-1,-1)
+    if (y0 == 0 && (x + 2 == nx || !has2)) out[-pitch + nx] = has2 ? p[2] : s.y;  // corner (nx,-1)
+    p += pitch;
+    double2 c = *reinterpret_cast<const double2*>(p);
+    double w = p[-1], e = p[2];
+#pragma unroll 4
+    for (int y = y0; y < y1; ++y) {
+        const double* pn = p + pitch;
+        const double2 n = *reinterpret_cast<const double2*>(pn);
+        const double wn = pn[-1], en = pn[2];
+        const double o0 = fused_update<kDiv>(c.x, w, c.y, s.x, n.x, k);
+        double* q = out + static_cast<int64_t>(y) * pitch + x;
+        if (has2) {
+            const double o1 = fused_update<kDiv>(c.y, c.x, e, s.y, n.y, k);
+            *reinterpret_cast<double2*>(q) = make_double2(o0, o1);
+            if (x + 2 == nx) q[2] = e;  // right ghost column
+        } else {
+            q[0] = o0;
+            q[1] = c.y;  // x == nx-1: the pair's second cell IS the right ghost
+        }
+        if (x == 0) q[-1] = w;  // left ghost column
+        if (y == 0) {           // bottom ghost row
+            if (has2)
+                *reinterpret_cast<double2*>(q - pitch) = s;
+            else
+                q[-pitch] = s.x;
+        }
+        if (y == ny - 1) {  // top ghost row (+ its two corners)
+            if (has2)
+                *reinterpret_cast<double2*>(q + pitch) = n;
+            else
+                q[pitch] = n.x;
+            if (x == 0) q[pitch - 1] = wn;
+            if (has2 && x + 2 == nx) q[pitch + 2] = en;
+            if (!has2) q[pitch + 1] = n.y;
+        }
+        s = c;
+        c = n;
+        w = wn;
+        e = en;
+        p = pn;
+    }
+}
+
+// ---- reductions -----------------------------------------------------------------------------
+
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// min/max over a w x hgt window starting at `f` (row pitch `pitch`); per-block partials to
+// part[2*b], part[2*b+1].  min and max are exact and order-independent, so the tree shape does not
+// matter for parity with std::min_element/std::max_element (main.cpp:74-75).
+__global__ void __launch_bounds__(256) k_minmax_partial(const double* __restrict__ f, int w, int hgt,
+                                                        int64_t pitch, double* __restrict__ part) {
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int j = blockIdx.x; j < hgt; j += gridDim.x) {
+        const double* row = f + static_cast<int64_t>(j) * pitch;
+        for (int i = threadIdx.x; i < w; i += blockDim.x) {
+            const double v = row[i];
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
+        }
+    }
+    __shared__ double slo[8], shi[8];
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lo = threadIdx.x < (blockDim.x >> 5) ? slo[threadIdx.x] : DBL_MAX;
+        hi = threadIdx.x < (blockDim.x >> 5) ? shi[threadIdx.x] : -DBL_MAX;
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (threadIdx.x == 0) {
+            part[2 * blockIdx.x] = lo;
+            part[2 * blockIdx.x + 1] = hi;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_minmax_final(const double* __restrict__ part, int nblocks,
+                                                      double* __restrict__ result) {
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+        lo = fmin(lo, part[2 * b]);
+        hi = fmax(hi, part[2 * b + 1]);
+    }
+    __shared__ double slo[8], shi[8];
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lo = threadIdx.x < (blockDim.x >> 5) ? slo[threadIdx.x] : DBL_MAX;
+        hi = threadIdx.x < (blockDim.x >> 5) ? shi[threadIdx.x] : -DBL_MAX;
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (threadIdx.x == 0) {
+            result[0] = lo;
+            result[1] = hi;
+        }
+    }
+}
+
+// max |u| and number of non-finite cells over the interior (stability diagnostic)
+__global__ void __launch_bounds__(256) k_health(const double* __restrict__ f, int nx, int ny, int64_t pitch,
+                                                double* __restrict__ max_abs_bits,
+                                                unsigned long long* __restrict__ nonfinite) {
+    double hi = 0.0;
+    unsigned long long bad = 0;
+    for (int j = blockIdx.x; j < ny; j += gridDim.x) {
+        const double* row = f + static_cast<int64_t>(j) * pitch;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+            const double v = row[i];
+            if (isfinite(v))
+                hi = fmax(hi, fabs(v));
+            else
+                ++bad;
+        }
+    }
+    hi = warp_max(hi);
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0) {
+        // non-negative doubles order like their bit patterns → integer atomicMax is exact
+        atomicMax(reinterpret_cast<unsigned long long*>(max_abs_bits),
+                  static_cast<unsigned long long>(__double_as_longlong(hi)));
+        if (bad) atomicAdd(nonfinite, bad);
+    }
+}
+
+StepK make_consts(double dx, double dy, double D, double vx, double vy, double dt, int flags, bool* use_div) {
+    StepK k;
+    k.dtD = dt * D;  // "dt * D * lap" groups as (dt*D)*lap, src/diffusion.cpp:14
+    k.ndt = -dt;     // src/advection.cpp:31
+    k.vx = vx;
+    k.vy = vy;
+    k.dx2 = dx * dx;  // src/diffusion.cpp:12
+    k.dy2 = dy * dy;  // src/diffusion.cpp:13
+    k.dx = dx;
+    k.dy = dy;
+    k.rdx2 = 1.0 / k.dx2;
+    k.rdy2 = 1.0 / k.dy2;
+    k.rdx = 1.0 / dx;
+    k.rdy = 1.0 / dy;
+    k.vx_pos = vx >= 0.0 ? 1 : 0;  // src/advection.cpp:16
+    k.vy_pos = vy >= 0.0 ? 1 : 0;  // src/advection.cpp:23
+    const bool exact = is_pow2(k.dx2) && is_pow2(k.dy2) && is_pow2(dx) && is_pow2(dy);
+    *use_div = !(exact || (flags & CSIM_STEP_FAST_RECIP));
+    return k;
+}
+
+int launch_boundary(csim_field* f, const int nbr[4], const int bc[4], double value) {
+    csim_ctx* c = f->ctx;
+    int mode[4];
+    for (int s = 0; s < 4; ++s) {
+        CSIM_REQUIRE(bc[s] >= 0 && bc[s] <= 2, CSIM_ERR_INVALID, "apply_boundary: unknown BC type");
+        mode[s] = (nbr[s] == CSIM_PROC_NULL && bc[s] != CSIM_BC_PERIODIC) ? bc[s] : -1;
+    }
+    double* f00 = f->at(0, 0);
+    if (mode[0] >= 0 || mode[1] >= 0) {
+        const int n = f->h + f->ny + 1;
+        CSIM_LAUNCH(c, k_bc_columns, (n + 255) / 256, 256, 0, f00, f->nx, f->ny, f->h, f->pitch, mode[0],
+                    mode[1], value);
+    }
+    if (mode[2] >= 0 || mode[3] >= 0) {
+        const int n = f->nxt();
+        CSIM_LAUNCH(c, k_bc_rows, (n + 255) / 256, 256, 0, f00, f->nx, f->ny, f->h, f->pitch, mode[2],
+                    mode[3], value);
+    }
+    return CSIM_OK;
+}
+
+int launch_step_v1(const csim_field* u, csim_field* out, const StepK& k, bool use_div) {
+    csim_ctx* c = u->ctx;
+    const dim3 block(32, 8);
+    const dim3 grid((u->nx + 63) / 64, (u->ny + 8 * kRowsV1 - 1) / (8 * kRowsV1));
+    if (use_div)
+        CSIM_LAUNCH(c, k_step_v1<true>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny, u->pitch, k);
+    else
+        CSIM_LAUNCH(c, k_step_v1<false>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny, u->pitch,
+                    k);
+    return CSIM_OK;
+}
+
+static int check_pair(const csim_field* u, const csim_field* out, const char* who) {
+    CSIM_REQUIRE(u != nullptr && out != nullptr, CSIM_ERR_INVALID, std::string(who) + ": null field");
+    CSIM_REQUIRE(u->ctx == out->ctx, CSIM_ERR_INVALID, std::string(who) + ": fields belong to different contexts");
+    CSIM_REQUIRE(u->nx == out->nx && u->ny == out->ny && u->h == out->h, CSIM_ERR_INVALID,
+                 std::string(who) + ": fields differ in geometry");
+    CSIM_REQUIRE(u->base != out->base, CSIM_ERR_INVALID, std::string(who) + ": u and out alias");
+    // with h == 0 the reference reads at(i-1,…) out of range and throws std::out_of_range
+    CSIM_REQUIRE(u->h >= 1 || u->nx == 0 || u->ny == 0, CSIM_ERR_RANGE, "Field index out of range");
+    return CSIM_OK;
+}
+
+}  // namespace csim
+
+using namespace csim;
+
+extern "C" {
+
+int csim_diffusion_step(const csim_field* u, csim_field* out, double D, double dt) {
+    if (int rc = check_pair(u, out, "csim_diffusion_step")) return rc;
+    csim_ctx* c = u->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    bool use_div = false;
+    const StepK k = make_consts(u->dx, u->dy, D, 0.0, 0.0, dt, 0, &use_div);
+    if (u->nx > 0 && u->ny > 0) {
+        const dim3 block(64, 4);
+        const dim3 grid((u->nx + 63) / 64, (u->ny + 3) / 4);
+        if (use_div)
+            CSIM_LAUNCH(c, k_diffusion<true>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny,
+                        u->pitch, k);
+        else
+            CSIM_LAUNCH(c, k_diffusion<false>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny,
+                        u->pitch, k);
+    }
+    const int n = u->nxt() > u->nyt() ? u->nxt() : u->nyt();
+    if (n > 0 && u->nxt() > 0 && u->nyt() > 0)
+        CSIM_LAUNCH(c, k_ring_copy, (n + 255) / 256, 256, 0, u->at(0, 0), out->at(0, 0), u->nxt(), u->nyt(),
+                    u->pitch);
+    return CSIM_OK;
+}
+
+int csim_advection_step(const csim_field* u, csim_field* out, double vx, double vy, double dt) {
+    if (int rc = check_pair(u, out, "csim_advection_step")) return rc;
+    csim_ctx* c = u->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    bool use_div = false;
+    const StepK k = make_consts(u->dx, u->dy, 0.0, vx, vy, dt, 0, &use_div);
+    if (u->nx > 0 && u->ny > 0) {
+        const dim3 block(64, 4);
+        const dim3 grid((u->nx + 63) / 64, (u->ny + 3) / 4);
+        if (use_div)
+            CSIM_LAUNCH(c, k_advection<true>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny,
+                        u->pitch, k);
+        else
+            CSIM_LAUNCH(c, k_advection<false>, grid, block, 0, u->interior(), out->interior(), u->nx, u->ny,
+                        u->pitch, k);
+    }
+    return CSIM_OK;
+}
+
+int csim_apply_boundary(csim_field* f, const int nbr[4], const int bc[4], double value) {
+    CSIM_REQUIRE(f != nullptr && nbr != nullptr && bc != nullptr, CSIM_ERR_INVALID,
+                 "csim_apply_boundary: null argument");
+    CSIM_CUDA(cudaSetDevice(f->ctx->device));
+    return launch_boundary(f, nbr, bc, value);
+}
+
+int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, int nsteps) {
+    if (int rc = check_pair(u, tmp, "csim_step_fused")) return rc;
+    CSIM_REQUIRE(p != nullptr && nsteps >= 0, CSIM_ERR_INVALID, "csim_step_fused: bad arguments");
+    CSIM_REQUIRE(u->h == 1, CSIM_ERR_UNSUPPORTED, "csim_step_fused: the fused path needs halo == 1 (main.cpp:65)");
+    csim_ctx* c = u->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    bool use_div = false;
+    const StepK k = make_consts(u->dx, u->dy, p->D, p->vx, p->vy, p->dt, p->flags, &use_div);
+    for (int n = 0; n < nsteps; ++n) {
+        if (int rc = launch_boundary(u, p->nbr, p->bc, p->bc_value)) return rc;  // main.cpp:102
+        if (u->nx > 0 && u->ny > 0)
+            if (int rc = launch_step_v1(u, tmp, k, use_div)) return rc;  // main.cpp:104-107 in one sweep
+        csim_field_swap(u, tmp);                                        // main.cpp:109
+    }
+    return CSIM_OK;
+}
+
+int csim_minmax(const csim_field* f, double* mn, double* mx) {
+    CSIM_REQUIRE(f != nullptr && mn != nullptr && mx != nullptr, CSIM_ERR_INVALID, "csim_minmax: null argument");
+    CSIM_REQUIRE(f->nxt() > 0 && f->nyt() > 0, CSIM_ERR_INVALID, "csim_minmax: empty field");
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    int nblocks = c->sm_count * 4;
+    if (nblocks > f->nyt()) nblocks = f->nyt();
+    if (static_cast<size_t>(2 * nblocks + 2) > c->scratch_doubles) nblocks = static_cast<int>(c->scratch_doubles / 2 - 1);
+    CSIM_LAUNCH(c, k_minmax_partial, nblocks, 256, 0, f->at(0, 0), f->nxt(), f->nyt(), f->pitch, c->d_scratch + 2);
+    CSIM_LAUNCH(c, k_minmax_final, 1, 256, 0, c->d_scratch + 2, nblocks, c->d_scratch);
+    CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, c->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    *mn = c->h_scratch[0];
+    *mx = c->h_scratch[1];
+    return CSIM_OK;
+}
+
+int csim_field_health(const csim_field* f, double* max_abs, uint64_t* nonfinite) {
+    CSIM_REQUIRE(f != nullptr && max_abs != nullptr && nonfinite != nullptr, CSIM_ERR_INVALID,
+                 "csim_field_health: null argument");
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    CSIM_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
+    if (f->nx > 0 && f->ny > 0) {
+        int nblocks = c->sm_count * 4;
+        if (nblocks > f->ny) nblocks = f->ny;
+        CSIM_LAUNCH(c, k_health, nblocks, 256, 0, f->interior(), f->nx, f->ny, f->pitch, c->d_scratch,
+                    reinterpret_cast<unsigned long long*>(c->d_scratch + 1));
+    }
+    CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, c->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    *max_abs = c->h_scratch[0];
+    std::memcpy(nonfinite, &c->h_scratch[1], sizeof(uint64_t));
+    return CSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""CPU-only checks of the product library: the C ABI exports what include/csim.h declares, the
+host-side functions (decomposition, stability limit, initial condition, BC names) agree with the
+oracle, and compute entry points fail loudly without a GPU instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits_equal
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "csim.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(csim_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(csim):
+    names = declared_functions()
+    assert len(names) >= 30
+    L = ctypes.CDLL(csim.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert csim.lib().csim_abi_version() == 1
+
+
+def test_decomp_matches_oracle(csim, port):
+    for size in (1, 2, 3, 4, 6, 8, 12, 16):
+        for (nxg, nyg) in ((16, 12), (130, 67), (8192, 8192)):
+            o = port.decomp(size, nxg, nyg)
+            for r in range(size):
+                d = csim.Decomp2D.init(size, r, nxg, nyg)
+                assert d.dims == o[r]["dims"] and d.coords == o[r]["coords"]
+                assert d.nbr_lr == o[r]["nbr_lr"] and d.nbr_du == o[r]["nbr_du"]
+                assert (d.nx_local, d.ny_local, d.x_offset, d.y_offset) == (
+                    o[r]["nx_local"], o[r]["ny_local"], o[r]["x_offset"], o[r]["y_offset"])
+    with pytest.raises(csim.CsimError):
+        csim.Decomp2D.init(4, 4, 8, 8)
+
+
+def test_safe_dt_matches_oracle(csim, port):
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        dx, dy = rng.uniform(0.1, 3, 2)
+        vx, vy = rng.uniform(-2, 2, 2) * (rng.random(2) > 0.2)
+        D = rng.uniform(0, 2) * (rng.random() > 0.2)
+        assert csim.safe_dt(dx, dy, vx, vy, D) == port.safe_dt(dx, dy, vx, vy, D)
+    assert csim.safe_dt(1, 1, 0.5, 0.0, 0.05) == 2.0
+
+
+def test_initial_condition_matches_reference_bits(csim, oracle_mod, port):
+    """src/init.cpp:12-33 through the product's host IC == oracle frame 0, per rank tile."""
+    for (nxg, nyg, size) in ((64, 64, 1), (50, 35, 6), (512, 512, 4)):
+        p = oracle_mod.SimParams(nx=nxg, ny=nyg, steps=1, out_every=1, sigma_frac=0.07, xc_frac=0.4,
+                                 yc_frac=0.6, A=1.5, dx=0.5, dy=2.0)
+        frame0 = port.run(p, nranks=1)["frames"][0]
+        for r in range(size):
+            d = csim.Decomp2D.init(size, r, nxg, nyg)
+            t = csim.initial_condition_host(d, 1, p.dx, p.dy, "gaussian_hotspot", p.A, p.sigma_frac,
+                                            p.xc_frac, p.yc_frac)
+            assert np.all(t[0] == 0) and np.all(t[:, 0] == 0)  # ghosts untouched
+            want = frame0[d.y_offset:d.y_offset + d.ny_local, d.x_offset:d.x_offset + d.nx_local]
+            assert bits_equal(t[1:-1, 1:-1], want)
+    z = csim.initial_condition_host(csim.Decomp2D.single(8, 8), 1, 1.0, 1.0, "constant_zero")
+    assert not z.any()
+    with pytest.raises(RuntimeError, match="Unknown IC preset"):
+        csim.initial_condition_host(csim.Decomp2D.single(8, 8), 1, 1.0, 1.0, "checkerboard")
+
+
+def test_bc_strings(csim):
+    """src/io.cpp:35-56"""
+    B = csim.BCType
+    assert csim.bc_from_string("Dirichlet") == B.Dirichlet and csim.bc_from_string("fixed") == B.Dirichlet
+    assert csim.bc_from_string("NOFLUX") == B.Neumann and csim.bc_from_string("zero-flux") == B.Neumann
+    assert csim.bc_from_string("period") == B.Periodic
+    assert [csim.bc_to_string(b) for b in B] == ["dirichlet", "neumann", "periodic"]
+    with pytest.raises(RuntimeError, match="Unknown BC type"):
+        csim.bc_from_string("robin")
+
+
+def test_no_cpu_fallback(csim):
+    """Without a device the product refuses to run; it never routes through oracle/."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(csim.CsimError, match="no CUDA device"):
+        csim.Context(0)
+
+
+def test_product_never_imports_oracle():
+    """No source file of the product package imports, includes, links or dlopens anything of oracle/."""
+    pkg = os.path.join(ROOT, "climate-sim-mpi-cpp_b200")
+    bad = re.compile(r"(import\s+oracle|from\s+oracle|cpu_oracle|liboracle|libcsim_ref|#include\s*[<\"].*oracle|oracle_port)")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not bad.search(text), f
