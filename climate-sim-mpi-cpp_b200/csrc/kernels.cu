@@ -12,10 +12,12 @@
 // value, same rounding); any other spacing keeps IEEE division unless CSIM_STEP_FAST_RECIP is set.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "csim_internal.hpp"
 #include "step_math.cuh"
+#include "step_tb_inst.cuh"
 
 namespace csim {
 
@@ -309,6 +311,103 @@ int launch_step_v1(const csim_field* u, csim_field* out, const StepK& k, bool us
     return CSIM_OK;
 }
 
+// ---- temporally blocked sweep (step_tb.cuh): host-side geometry and dispatch ---------------------
+
+static int tb_max_T() {
+    static int cached = -1;
+    if (cached < 0) {
+        cached = 3;  // T = 4 spills registers and measures slower (profiles/r01_tb_tuning.md)
+        if (const char* e = std::getenv("CSIM_TB_MAXT")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= kTbMaxT) cached = v;
+        }
+    }
+    return cached;
+}
+static int tb_env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// Advance `u` by T steps into `out` in one sweep.  nbr/bc as in csim_step_params.  Sides with a
+// neighbour are read as they are in memory (one ghost line), so T must be 1 there.
+int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
+                   int T) {
+    csim_ctx* c = u->ctx;
+    const int nx = u->nx, ny = u->ny;
+    TbArgs a;
+    a.u = u->interior();
+    a.out = out->interior();
+    a.pitch = u->pitch;
+    a.nx = nx;
+    a.ny = ny;
+    a.phys = 0;
+    for (int s = 0; s < 4; ++s)
+        if (p->nbr[s] == CSIM_PROC_NULL) a.phys |= 1 << s;
+    const bool pl = a.phys & 1, pr = a.phys & 2, pb = a.phys & 4, pt = a.phys & 8;
+    CSIM_REQUIRE(T == 1 || a.phys == 15, CSIM_ERR_INVALID, "launch_step_tb: T > 1 needs all sides physical");
+    a.xlo = 0;
+    a.xhi = nx;
+    a.ylo = 0;
+    a.yhi = ny;
+    a.sx0 = pl ? -1 : 0;
+    a.sx1 = pr ? nx + 1 : nx;
+    a.sy0 = pb ? -1 : 0;
+    a.sy1 = pt ? ny + 1 : ny;
+    a.fx0 = pl ? 1 : a.xlo;
+    a.fx1 = pr ? nx - 1 : a.xhi;
+    a.fy0 = pb ? 1 : a.ylo;
+    a.fy1 = pt ? ny - 1 : a.yhi;
+    a.bcL = p->bc[0];
+    a.bcR = p->bc[1];
+    a.bcB = p->bc[2];
+    a.bcT = p->bc[3];
+    a.value = p->bc_value;
+    a.k = k;
+    a.xmax_load = static_cast<int>(u->pitch) - kLeadX;
+    a.pf_rows = tb_env_int("CSIM_TB_PF", 4);
+    a.row_limit = a.pf_rows > 0 ? ny + kLeadY : -(1 << 30);  // <= 0 disables the prefetch branch
+    if (a.pf_rows < 0) a.pf_rows = 0;
+    a.nstrips = (nx + kTbWout - 1) / kTbWout;
+    if (a.nstrips < 1) a.nstrips = 1;
+    a.edge_split = tb_env_int("CSIM_TB_EDGE_SPLIT", 2);
+    if (a.edge_split < 1) a.edge_split = 1;
+    // chunk height: fill k whole rounds of the resident warp slots of the machine
+    const int rows = a.sy1 - a.sy0;
+    const int n_edge = a.nstrips >= 2 ? 2 : 1, n_int = a.nstrips - n_edge;
+    const int slots = c->sm_count * kTbBlocksPerSM * kTbWarpsPerBlock;
+    const int weight = n_int + n_edge * a.edge_split;
+    // Chunk height.  A launch runs as several rounds of resident warps; short chunks keep the last
+    // round from idling the machine, tall chunks amortise the 2T rows each chunk re-computes.
+    // Measured on B200 at 8192^2 (profiles/r01_tb_tuning.md): 64-128 rows is the flat optimum.
+    int ch = tb_env_int("CSIM_TB_CHUNK", 0);
+    if (ch <= 0) {
+        const long long want = static_cast<long long>(rows) * weight / (2LL * slots);  // >= 2 rounds
+        ch = static_cast<int>(want < 32 ? 32 : (want > 96 ? 96 : want));
+    }
+    if (ch > rows) ch = rows;
+    if (ch < 1) ch = 1;
+    a.chunk_h = ch;
+    a.nchunks = (rows + ch - 1) / ch;
+    const int eh = (ch + a.edge_split - 1) / a.edge_split;
+    const int nch_edge = (rows + eh - 1) / eh;
+    a.n_edge_items = n_edge * nch_edge;
+    a.n_items = n_int * a.nchunks + a.n_edge_items;
+    cudaError_t e;
+    const bool vxp = k.vx_pos != 0, vyp = k.vy_pos != 0;
+    if (vxp && vyp)
+        e = tb_launch_pp(T, mode, a, c->stream);
+    else if (vxp)
+        e = tb_launch_pn(T, mode, a, c->stream);
+    else if (vyp)
+        e = tb_launch_np(T, mode, a, c->stream);
+    else
+        e = tb_launch_nn(T, mode, a, c->stream);
+    ++c->launches;
+    if (e != cudaSuccess) return cuda_fail(e, "k_step_tb", __FILE__, __LINE__);
+    return CSIM_OK;
+}
+
 static int check_pair(const csim_field* u, const csim_field* out, const char* who) {
     CSIM_REQUIRE(u != nullptr && out != nullptr, CSIM_ERR_INVALID, std::string(who) + ": null field");
     CSIM_REQUIRE(u->ctx == out->ctx, CSIM_ERR_INVALID, std::string(who) + ": fields belong to different contexts");
@@ -383,11 +482,35 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     CSIM_CUDA(cudaSetDevice(c->device));
     bool use_div = false;
     const StepK k = make_consts(u->dx, u->dy, p->D, p->vx, p->vy, p->dt, p->flags, &use_div);
-    for (int n = 0; n < nsteps; ++n) {
-        if (int rc = launch_boundary(u, p->nbr, p->bc, p->bc_value)) return rc;  // main.cpp:102
-        if (u->nx > 0 && u->ny > 0)
-            if (int rc = launch_step_v1(u, tmp, k, use_div)) return rc;  // main.cpp:104-107 in one sweep
-        csim_field_swap(u, tmp);                                        // main.cpp:109
+    for (int s = 0; s < 4; ++s)
+        CSIM_REQUIRE(p->bc[s] >= 0 && p->bc[s] <= 2, CSIM_ERR_INVALID, "csim_step_fused: unknown BC type");
+    if (u->nx == 0 || u->ny == 0) {  // nothing to advance; keep the reference's swap parity
+        if (nsteps & 1) csim_field_swap(u, tmp);
+        return CSIM_OK;
+    }
+    if (p->flags & CSIM_STEP_NO_TEMPORAL) {
+        // plain path: boundary kernels + one-step sweep (independent implementation, kept as a
+        // cross-check of the blocked kernel)
+        for (int n = 0; n < nsteps; ++n) {
+            if (int rc = launch_boundary(u, p->nbr, p->bc, p->bc_value)) return rc;  // main.cpp:102
+            if (int rc = launch_step_v1(u, tmp, k, use_div)) return rc;              // main.cpp:104-107
+            csim_field_swap(u, tmp);                                                 // main.cpp:109
+        }
+        return CSIM_OK;
+    }
+    const bool unit = k.rdx2 == 1.0 && k.rdy2 == 1.0 && k.rdx == 1.0 && k.rdy == 1.0;
+    const int mode = use_div ? MODE_DIV : (unit ? MODE_UNIT : MODE_RECIP);
+    bool all_phys = true;
+    for (int s = 0; s < 4; ++s) all_phys = all_phys && p->nbr[s] == CSIM_PROC_NULL;
+    // IEEE division is compute-bound: blocking in time buys nothing there.  Tiles with neighbours
+    // carry one ghost line per exchange, so they advance one step per sweep.
+    const int maxT = (mode == MODE_DIV || !all_phys) ? 1 : tb_max_T();
+    int left = nsteps;
+    while (left > 0) {
+        const int T = left < maxT ? left : maxT;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T)) return rc;
+        csim_field_swap(u, tmp);
+        left -= T;
     }
     return CSIM_OK;
 }

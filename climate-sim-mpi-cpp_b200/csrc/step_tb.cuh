@@ -1,0 +1,322 @@
+// step_tb.cuh — the hot kernel: fused diffusion+advection, T time steps per sweep over HBM.
+//
+// Design: one WARP owns a strip of 128 columns (4 cells per lane, one 256-bit
+// load per lane per row) and streams down a chunk of rows.  For every time level k < T the warp
+// keeps the two most recent rows of that level in registers; when row r of level 0 arrives from
+// HBM it produces row r-1 of level 1, from that row r-2 of level 2, … and finally stores row r-T of
+// level T.  x-neighbours cross lanes with two 64-bit shuffles per level-row; nothing goes through
+// shared memory and warps never synchronise with each other.  Each level loses one column of
+// validity on both strip edges, so a strip yields 120 finished columns out of 128 (T <= 4) and a
+// chunk re-computes T rows above and below itself.  Every cell is read from HBM once and written
+// once per T steps: 16/T bytes per cell update instead of 16.
+//
+// Boundaries are folded into the sweep (no separate apply_boundary pass, no std::copy):
+//   - cells outside [xlo,xhi) x [ylo,yhi) keep their value from level to level (that is what
+//     "Periodic" means in the reference: ghosts are frozen), except that ghost
+//     cells of a physical Dirichlet/Neumann side take the value apply_boundary (boundary.cpp:23-53)
+//     would have written before the step, so the ring of `out` is what diffusion.cpp:18-25 copies;
+//   - cells on the first/last interior line of a physical side read `value` (Dirichlet) or their
+//     own value (Neumann mirror) instead of the neighbour.
+// These fix-ups run only in the two edge strips and in the first/last row of the tile; interior
+// level-rows take a branch-free fast path.
+//
+// Arithmetic: tb_update issues exactly the reference's operations in the reference's order with
+// non-contractible round-to-nearest intrinsics (see step_math.cuh); MODE_UNIT drops the four
+// multiplications by 1.0 (dx = dy = 1), which are exact identities.
+#pragma once
+#include <cstdint>
+
+#include "step_math.cuh"
+
+namespace csim {
+
+constexpr int kTbCells = 4;                        // cells per lane
+constexpr int kTbWidth = 32 * kTbCells;            // 128 columns per strip
+constexpr int kTbHX = 4;                           // columns discarded on each strip edge
+constexpr int kTbWout = kTbWidth - 2 * kTbHX;      // 120 finished columns per strip
+constexpr int kTbMaxT = 4;                         // T <= kTbHX
+constexpr int kTbWarpsPerBlock = 4;
+constexpr int kTbBlocksPerSM = 3;                  // 168 registers per thread, 12 warps per SM
+
+enum { MODE_UNIT = 0, MODE_RECIP = 1, MODE_DIV = 2 };
+
+struct TbArgs {
+    const double* u;   // level-0 field, pointer to interior cell (0,0)
+    double* out;       // level-T field, pointer to interior cell (0,0)
+    long long pitch;   // doubles per row
+    int nx, ny;        // interior size of the tile
+    int xlo, xhi, ylo, yhi;  // cells advanced by the stencil: xlo<=x<xhi, ylo<=y<yhi
+    int sx0, sx1, sy0, sy1;  // cells stored (ghost lines of physical sides included)
+    int fx0, fx1, fy0, fy1;  // cells that need no boundary fix-up (fast path)
+    int nstrips;       // strips across x
+    int nchunks;       // chunks down y for interior strips
+    int chunk_h;       // rows per chunk (interior strips); edge strips use chunk_h / edge_split
+    int edge_split;
+    int n_items;       // total (strip, chunk) work items
+    int n_edge_items;  // of which the first n_edge_items belong to the edge strips
+    int xmax_load;     // a lane may load its 4 cells iff x0+3 < xmax_load (row allocation bound)
+    int pf_rows;       // L2 prefetch distance in rows (0 = off)
+    int row_limit;     // rows y < row_limit are inside the allocation
+    int phys;          // bit s: side s (left,right,bottom,top) is a physical boundary
+    int bcL, bcR, bcB, bcT;
+    double value;      // Dirichlet value
+    StepK k;
+};
+
+template <int MODE, bool VXP, bool VYP>
+__device__ __forceinline__ double tb_update(double c, double w, double e, double s, double n, const StepK& k) {
+    const double c2 = __dmul_rn(2.0, c);
+    double lx = __dadd_rn(__dsub_rn(e, c2), w);
+    double ly = __dadd_rn(__dsub_rn(n, c2), s);
+    if (MODE == MODE_RECIP) {
+        lx = __dmul_rn(lx, k.rdx2);
+        ly = __dmul_rn(ly, k.rdy2);
+    } else if (MODE == MODE_DIV) {
+        lx = __ddiv_rn(lx, k.dx2);
+        ly = __ddiv_rn(ly, k.dy2);
+    }
+    const double o = __dadd_rn(c, __dmul_rn(k.dtD, __dadd_rn(lx, ly)));
+    double ddx = VXP ? __dsub_rn(c, w) : __dsub_rn(e, c);
+    double ddy = VYP ? __dsub_rn(c, s) : __dsub_rn(n, c);
+    if (MODE == MODE_RECIP) {
+        ddx = __dmul_rn(ddx, k.rdx);
+        ddy = __dmul_rn(ddy, k.rdy);
+    } else if (MODE == MODE_DIV) {
+        ddx = __ddiv_rn(ddx, k.dx);
+        ddy = __ddiv_rn(ddy, k.dy);
+    }
+    const double adv = __dadd_rn(__dmul_rn(k.vx, ddx), __dmul_rn(k.vy, ddy));
+    return __dadd_rn(o, __dmul_rn(k.ndt, adv));
+}
+
+// Dirichlet → value, Neumann → mirror, Periodic → keep
+__device__ __forceinline__ double bc_pick(int bc, double value, double mirror, double keep) {
+    return bc == 0 ? value : (bc == 1 ? mirror : keep);
+}
+
+// Per-lane, per-work-item constants of the boundary fix-ups (only read on the general path).
+struct TbLane {
+    int x0;        // x of the lane's cell 0 (always a multiple of 4)
+    int inx;       // bit i: cell i lies in [xlo, xhi) and is advanced by the stencil
+    bool at_l;     // cell 0 is x == 0 on a physical left side      → its west neighbour is the BC
+    bool ghost_l;  // cell 3 is x == -1 on a physical left side     → ghost rule
+    int at_r;      // index of the cell with x == nx-1 on a physical right side, or -1
+    int ghost_r;   // index of the cell with x == nx   on a physical right side, or -1
+};
+
+// One row of one level.  s/c/n are rows j-1, j, j+1 of the current level; the result is row j of
+// the next level.  GEN = false: the plain stencil on all four cells (interior strips, interior
+// rows).  GEN = true: every boundary rule of the reference (see the file header); all conditions on
+// j are warp-uniform, all conditions on x are per-lane selects, so the four stencils still
+// interleave.
+template <int MODE, bool VXP, bool VYP, bool GEN>
+__device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j, const double (&s)[4],
+                                       const double (&c)[4], const double (&n)[4], double (&res)[4]) {
+    const double w0 = __shfl_up_sync(0xffffffffu, c[3], 1);
+    const double e3 = __shfl_down_sync(0xffffffffu, c[0], 1);
+    if (!GEN) {
+        res[0] = tb_update<MODE, VXP, VYP>(c[0], w0, c[1], s[0], n[0], a.k);
+        res[1] = tb_update<MODE, VXP, VYP>(c[1], c[0], c[2], s[1], n[1], a.k);
+        res[2] = tb_update<MODE, VXP, VYP>(c[2], c[1], c[3], s[2], n[2], a.k);
+        res[3] = tb_update<MODE, VXP, VYP>(c[3], c[2], e3, s[3], n[3], a.k);
+        return;
+    }
+    const bool physB = a.phys & 4, physT = a.phys & 8;
+    if (j < a.ylo || j >= a.yhi) {  // warp-uniform: the row is not advanced (ghost row, padding)
+        const bool gb = physB && j == -1, gt = physT && j == a.ny;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double r = c[i];
+            const bool in = (ln.inx >> i) & 1;
+            // ghost rows of physical Dirichlet/Neumann sides take what apply_boundary wrote into u
+            // before this step (diffusion_step then copies it into out's ring)
+            if (gb && in) r = bc_pick(a.bcB, a.value, n[i], r);
+            if (gt && in) r = bc_pick(a.bcT, a.value, s[i], r);
+            res[i] = r;
+        }
+        return;
+    }
+    // first/last interior row of a physical side: the neighbour row is the boundary value
+    double ss[4], nn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ss[i] = s[i];
+        nn[i] = n[i];
+    }
+    if (physB && j == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ss[i] = bc_pick(a.bcB, a.value, c[i], s[i]);
+    }
+    if (physT && j == a.ny - 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nn[i] = bc_pick(a.bcT, a.value, c[i], n[i]);
+    }
+    // x direction: only a few (lane, cell) pairs differ from the plain stencil
+    double ww0 = w0;
+    double ee[4] = {c[1], c[2], c[3], e3};
+    double keep[4] = {c[0], c[1], c[2], c[3]};  // value of cells that are not advanced (frozen)
+    if (ln.at_l) ww0 = bc_pick(a.bcL, a.value, c[0], w0);         // x == 0: west neighbour is the BC
+    if (ln.ghost_l) keep[3] = bc_pick(a.bcL, a.value, e3, c[3]);  // x == -1: ghost rule
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i == ln.at_r) ee[i] = bc_pick(a.bcR, a.value, c[i], ee[i]);  // x == nx-1: east neighbour is the BC
+        if (i == ln.ghost_r) keep[i] = bc_pick(a.bcR, a.value, i == 0 ? w0 : c[i == 0 ? 0 : i - 1], c[i]);  // x == nx
+    }
+    double r[4];
+    r[0] = tb_update<MODE, VXP, VYP>(c[0], ww0, ee[0], ss[0], nn[0], a.k);
+    r[1] = tb_update<MODE, VXP, VYP>(c[1], c[0], ee[1], ss[1], nn[1], a.k);
+    r[2] = tb_update<MODE, VXP, VYP>(c[2], c[1], ee[2], ss[2], nn[2], a.k);
+    r[3] = tb_update<MODE, VXP, VYP>(c[3], c[2], ee[3], ss[3], nn[3], a.k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) res[i] = ((ln.inx >> i) & 1) ? r[i] : keep[i];
+}
+
+__device__ __forceinline__ void tb_load4(const double* p, bool ok, double (&v)[4]) {
+    if (ok) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                     : "l"(p));
+    } else {
+        v[0] = v[1] = v[2] = v[3] = 0.0;
+    }
+}
+__device__ __forceinline__ void tb_prefetch_l2(const double* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void tb_store4(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
+                 : "memory");
+}
+
+// Store row `jo` of level T (held in v) if it belongs to this work item.
+__device__ __forceinline__ void tb_store_row(const TbArgs& a, const TbLane& ln, int lane, bool lane_store_all,
+                                             int jo, int ya, int yb, const double (&v)[4]) {
+    if (jo < ya || jo >= yb) return;  // warp-uniform
+    double* dst = a.out + static_cast<long long>(jo) * a.pitch + ln.x0;
+    const bool ring_row = jo < 0 || jo >= a.ny;
+    if (lane_store_all && !ring_row) {
+        tb_store4(dst, v);
+    } else {
+        const int lo = ring_row ? max(a.sx0, 0) : a.sx0;  // ring rows: no corners
+        const int hi = ring_row ? min(a.sx1, a.nx) : a.sx1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = ln.x0 + i, pos = lane * kTbCells + i;
+            const bool zone = (pos >= kTbHX && pos < kTbWidth - kTbHX) || x == -1 || x == a.nx;
+            if (zone && x >= lo && x < hi) dst[i] = v[i];
+        }
+    }
+}
+
+// One tick: two new level-0 rows (r, r+1) enter, two finished rows (r-T, r-T+1) leave.
+// st[k][slot][row][cell]: per level two slots of two rows.  In phase PH, slot PH of every level is its
+// state (rows r-k-2, r-k-1) and slot 1-PH its incoming pair (rows r-k, r-k+1); afterwards the
+// incoming pair is the state and slot PH is free for the next pair, so consecutive ticks alternate PH
+// and no register is ever moved.
+template <int T, int MODE, bool VXP, bool VYP, int PH, bool GEN>
+__device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int lane, bool lane_store_all,
+                                        bool can_load, int r, int ya, int yb, const double*& src,
+                                        double (&st)[T][2][2][4]) {
+    double fin[2][4];
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        double(&A)[4] = st[k][PH][0];
+        double(&B)[4] = st[k][PH][1];
+        double(&C)[4] = st[k][1 - PH][0];
+        double(&D)[4] = st[k][1 - PH][1];
+        if (k + 1 < T) {
+            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k - 1, A, B, C, st[k + 1 < T ? k + 1 : k][1 - PH][0]);
+            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k, B, C, D, st[k + 1 < T ? k + 1 : k][1 - PH][1]);
+        } else {
+            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k - 1, A, B, C, fin[0]);
+            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k, B, C, D, fin[1]);
+        }
+        if (k == 0) {
+            // rows r-2, r-1 of level 0 are dead now: prefetch rows r+2, r+3 into their registers
+            tb_load4(src, can_load, A);
+            tb_load4(src + a.pitch, can_load, B);
+            // pull the rows pf_rows ahead into L2 (costs no registers; clamped to the allocation)
+            if (can_load && r + 3 + a.pf_rows < a.row_limit) {
+                tb_prefetch_l2(src + static_cast<long long>(a.pf_rows) * a.pitch);
+                tb_prefetch_l2(src + static_cast<long long>(a.pf_rows + 1) * a.pitch);
+            }
+            src += 2 * a.pitch;
+        }
+    }
+    tb_store_row(a, ln, lane, lane_store_all, r - T, ya, yb, fin[0]);
+    tb_store_row(a, ln, lane, lane_store_all, r - T + 1, ya, yb, fin[1]);
+}
+
+template <int T, int MODE, bool VXP, bool VYP>
+__global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_tb(const __grid_constant__ TbArgs a) {
+    static_assert(T >= 1 && T <= kTbMaxT, "T out of range");
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kTbWarpsPerBlock + (threadIdx.x >> 5);
+    if (item >= a.n_items) return;  // warp-uniform
+
+    // work item → (strip, first row, row count).  Interior strips get chunks of chunk_h rows; the
+    // (slower) edge strips get edge_split times as many chunks of chunk_h/edge_split rows.
+    int strip, ya, h;
+    {
+        // the slower edge-strip items come first so that they never form the tail of the launch
+        const int n_edge = a.nstrips >= 2 ? 2 : 1;
+        const int n_int = a.nstrips - n_edge;
+        if (item < a.n_edge_items) {
+            strip = (item % n_edge) ? a.nstrips - 1 : 0;
+            h = (a.chunk_h + a.edge_split - 1) / a.edge_split;
+            ya = a.sy0 + (item / n_edge) * h;
+        } else {
+            const int e = item - a.n_edge_items;
+            strip = 1 + e % n_int;
+            h = a.chunk_h;
+            ya = a.sy0 + (e / n_int) * h;
+        }
+    }
+    if (ya >= a.sy1) return;
+    const int yb = min(ya + h, a.sy1);
+    const int xb = strip * kTbWout - kTbHX;
+    TbLane ln;
+    ln.x0 = xb + lane * kTbCells;
+    const bool can_load = ln.x0 + 3 < a.xmax_load;
+    const bool strip_fast = xb >= a.fx0 && xb + kTbWidth <= a.fx1;
+    const bool lane_store_all = lane >= 1 && lane <= 30 && ln.x0 >= a.sx0 && ln.x0 + 3 < a.sx1;
+    {
+        const bool physL = a.phys & 1, physR = a.phys & 2;
+        ln.inx = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (ln.x0 + i >= a.xlo && ln.x0 + i < a.xhi) ln.inx |= 1 << i;
+        ln.at_l = physL && ln.x0 == 0;
+        ln.ghost_l = physL && ln.x0 + 3 == -1;
+        const int dr = a.nx - 1 - ln.x0, dg = a.nx - ln.x0;
+        ln.at_r = (physR && dr >= 0 && dr < 4) ? dr : -1;
+        ln.ghost_r = (physR && dg >= 0 && dg < 4) ? dg : -1;
+    }
+
+    double st[T][2][2][4];
+#pragma unroll
+    for (int k = 0; k < T; ++k)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) st[k][q >> 3][(q >> 2) & 1][q & 3] = 0.0;
+
+    int r = ya - T;
+    const double* src = a.u + static_cast<long long>(r) * a.pitch + ln.x0;
+    tb_load4(src, can_load, st[0][1][0]);
+    tb_load4(src + a.pitch, can_load, st[0][1][1]);
+    src += 2 * a.pitch;
+
+    // every tick touches rows r-T .. r+1; it is "fast" when all rows it produces are interior
+    const int r_end = yb + T;
+    for (; r < r_end; r += 4) {
+        if (strip_fast && r - T >= a.fy0 && r < a.fy1)
+            tb_tick<T, MODE, VXP, VYP, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+        else
+            tb_tick<T, MODE, VXP, VYP, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+        if (strip_fast && r + 2 - T >= a.fy0 && r + 2 < a.fy1)
+            tb_tick<T, MODE, VXP, VYP, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+        else
+            tb_tick<T, MODE, VXP, VYP, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+    }
+}
+
+}  // namespace csim

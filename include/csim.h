@@ -154,8 +154,10 @@ typedef struct csim_step_params {
 /* The fused time step — the body of the loop at src/main.cpp:101-109 without the exchange:
  *   apply_boundary(u) ; tmp := u ; diffusion_step(u,tmp) ; advection_step(u,tmp) ; swap(u,tmp)
  * repeated `nsteps` times in ONE pass per step over HBM (no separate copy, no second sweep).
- * On return (stream order) `u` holds the newest state and `tmp` the previous one, as after the
- * reference's swap.  Interior cells are bit-identical to the reference's; edge ghost cells hold
+ * On return (stream order) `u` holds the newest state, as after the reference's swap; `tmp` is
+ * scratch (the reference overwrites it at the top of every step, main.cpp:104).  The library may
+ * advance several steps per sweep over HBM (temporal blocking) where that leaves the result
+ * bit-identical.  Interior cells are bit-identical to the reference's; edge ghost cells hold
  * what the reference's would hold; corner ghosts are unspecified.
  * Sides with a neighbour (nbr != PROC_NULL) read their ghost line as the exchange left it, so
  * for multi-rank runs call csim_halo_exchange before each step (or use csim_run_steps). */
