@@ -65,6 +65,15 @@ int csim_ctx_create(int device, csim_ctx** out) {
     CSIM_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CSIM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // the exchange stream outranks the main stream so that its small kernels (pack, NCCL, unpack,
+        // frame sweep) are not queued behind the interior sweep that fills every SM
+        int lo = 0, hi = 0;
+        CSIM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CSIM_CUDA(cudaStreamCreateWithPriority(&c->stream_x, cudaStreamNonBlocking, hi));
+    }
+    CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->scratch_doubles = 4096;
     CSIM_CUDA(cudaMalloc(&c->d_scratch, c->scratch_doubles * sizeof(double)));
     CSIM_CUDA(cudaMallocHost(&c->h_scratch, c->scratch_doubles * sizeof(double)));
@@ -82,7 +91,14 @@ int csim_ctx_destroy(csim_ctx* c) {
     }
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->stream_x) {
+        cudaStreamSynchronize(c->stream_x);
+        cudaStreamDestroy(c->stream_x);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->d_pack) cudaFree(c->d_pack);
+    if (c->d_wide) cudaFree(c->d_wide);
     delete c;
     return CSIM_OK;
 }
@@ -91,6 +107,7 @@ int csim_sync(csim_ctx* c) {
     CSIM_REQUIRE(c != nullptr, CSIM_ERR_INVALID, "csim_sync: ctx is null");
     CSIM_CUDA(cudaSetDevice(c->device));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
     return CSIM_OK;
 }
 

@@ -31,6 +31,10 @@ struct csim_ctx {
     int comm_size = 1, comm_rank = 0;
     double* d_pack = nullptr;  // 4 column buffers: send L, send R, recv L, recv R
     size_t pack_doubles = 0;
+    double* d_wide = nullptr;  // wide-halo exchange staging: 8 send + 8 recv regions
+    size_t wide_doubles = 0;
+    cudaStream_t stream_x = nullptr;  // exchange + frame sweep, overlapped with the interior sweep
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 148;
 };
 
@@ -55,6 +59,15 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // 1/x is exact and x*(1/x)==1 iff x is a (normal) power of two
 bool is_pow2(double x);
+
+struct StepK;
+enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2 };
+int tb_max_T();
+bool tb_split_pointless(int nchunks, int n_int);
+// kernels.cu
+int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mode);
+int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
+                   int T, int part, cudaStream_t stream, bool* launched);
 
 }  // namespace csim
 

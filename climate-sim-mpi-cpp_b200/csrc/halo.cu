@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "csim_internal.hpp"
+#include "step_tb.cuh"
 
 namespace csim {
 
@@ -87,6 +88,111 @@ __global__ void k_unpack_columns(double* __restrict__ u, int nx, int ny, int64_t
     double* row = u + static_cast<int64_t>(j) * pitch;
     if (has_left) row[-1] = buf[2 * ny + j];
     if (has_right) row[nx] = buf[3 * ny + j];
+}
+
+// ---- wide exchange: T ghost lines from all eight neighbours, for the temporally blocked sweep ------
+// A sweep of T steps needs T valid lines around the tile, corners included.  Each rank packs eight
+// regions of its own tile (four bands of T lines, four T x T corners) into one staging buffer, all
+// sixteen transfers go out as one NCCL group, and one kernel scatters the received regions into the
+// ghost area.  Bands span the physical ghost line of a perpendicular physical side as well, because
+// "periodic" ghosts are frozen values that the neighbour's halo cells depend on.
+struct XRegion {
+    int x0, y0, w, h;  // interior coordinates of the region's first cell, extent
+    long long off;     // offset of the region in the staging buffer (doubles)
+    int peer;          // rank on the other side, -1: unused
+};
+struct XTable {
+    XRegion r[8];
+};
+
+__global__ void __launch_bounds__(256) k_pack_regions(const double* __restrict__ u, long long pitch, XTable t,
+                                                      double* __restrict__ buf) {
+    const XRegion g = t.r[blockIdx.y];
+    if (g.peer < 0) return;
+    const int n = g.w * g.h;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int yy = e / g.w, xx = e - yy * g.w;
+        buf[g.off + e] = u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx];
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_regions(double* __restrict__ u, long long pitch, XTable t,
+                                                        const double* __restrict__ buf) {
+    const XRegion g = t.r[blockIdx.y];
+    if (g.peer < 0) return;
+    const int n = g.w * g.h;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int yy = e / g.w, xx = e - yy * g.w;
+        u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx] = buf[g.off + e];
+    }
+}
+
+// Fill T ghost lines of `f` on every side that has a neighbour, on `stream`.
+static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream) {
+    csim_ctx* c = f->ctx;
+    const int nx = f->nx, ny = f->ny;
+    const int cx = dec->coords[0], cy = dec->coords[1];
+    auto rank_of = [&](int x, int y) {
+        return (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) ? -1 : x * dec->dims[1] + y;
+    };
+    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pr = dec->nbr[CSIM_RIGHT] == CSIM_PROC_NULL;
+    const bool pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL, pt = dec->nbr[CSIM_TOP] == CSIM_PROC_NULL;
+    // extent of a band along its own side: interior plus the ghost line of a physical end
+    const int bx0 = pl ? -1 : 0, bx1 = pr ? nx + 1 : nx;
+    const int by0 = pb ? -1 : 0, by1 = pt ? ny + 1 : ny;
+    XTable snd, rcv;
+    long long off = 0;
+    int k = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            XRegion s, r;
+            s.peer = r.peer = rank_of(cx + dx, cy + dy);
+            // what I send towards (dx,dy): my own cells next to that side
+            s.x0 = dx < 0 ? 0 : (dx > 0 ? nx - T : bx0);
+            s.w = dx != 0 ? T : bx1 - bx0;
+            s.y0 = dy < 0 ? 0 : (dy > 0 ? ny - T : by0);
+            s.h = dy != 0 ? T : by1 - by0;
+            // where what comes from (dx,dy) lands: my ghost area on that side
+            r.x0 = dx < 0 ? -T : (dx > 0 ? nx : bx0);
+            r.w = s.w;
+            r.y0 = dy < 0 ? -T : (dy > 0 ? ny : by0);
+            r.h = s.h;
+            s.off = off;
+            off += static_cast<long long>(s.w) * s.h;
+            snd.r[k] = s;
+            rcv.r[k] = r;
+            ++k;
+        }
+    const long long send_total = off;
+    for (int q = 0; q < 8; ++q) rcv.r[q].off = send_total + snd.r[q].off;
+    if (c->wide_doubles < static_cast<size_t>(2 * send_total)) {
+        if (c->d_wide) {
+            CSIM_CUDA(cudaDeviceSynchronize());
+            CSIM_CUDA(cudaFree(c->d_wide));
+            c->d_wide = nullptr;
+        }
+        CSIM_CUDA(cudaMalloc(&c->d_wide, static_cast<size_t>(2 * send_total) * sizeof(double)));
+        c->wide_doubles = static_cast<size_t>(2 * send_total);
+    }
+    double* buf = c->d_wide;
+    const dim3 grid(32, 8);
+    k_pack_regions<<<grid, 256, 0, stream>>>(f->interior(), f->pitch, snd, buf);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+    CSIM_NCCL(g_nccl.GroupStart());
+    for (int q = 0; q < 8; ++q) {
+        if (snd.r[q].peer < 0) continue;
+        const size_t n = static_cast<size_t>(snd.r[q].w) * snd.r[q].h;
+        CSIM_NCCL(g_nccl.Recv(buf + rcv.r[q].off, n, ncclDouble, rcv.r[q].peer, comm, stream));
+        CSIM_NCCL(g_nccl.Send(buf + snd.r[q].off, n, ncclDouble, snd.r[q].peer, comm, stream));
+    }
+    CSIM_NCCL(g_nccl.GroupEnd());
+    ++c->launches;
+    k_unpack_regions<<<grid, 256, 0, stream>>>(f->interior(), f->pitch, rcv, buf);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    return CSIM_OK;
 }
 
 }  // namespace csim
@@ -198,9 +304,44 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     for (int s = 0; s < 4; ++s)
         CSIM_REQUIRE(p->nbr[s] == dec->nbr[s], CSIM_ERR_INVALID,
                      "csim_run_steps: step params and decomposition disagree on neighbours");
-    for (int n = 0; n < nsteps; ++n) {
-        if (int rc = csim_halo_exchange(u, dec)) return rc;     // main.cpp:101
-        if (int rc = csim_step_fused(u, tmp, p, 1)) return rc;  // main.cpp:102-109
+    csim_ctx* c = u->ctx;
+    CSIM_REQUIRE(c == tmp->ctx && u->nx == tmp->nx && u->ny == tmp->ny && u->h == tmp->h && u->base != tmp->base,
+                 CSIM_ERR_INVALID, "csim_run_steps: fields differ in geometry or alias");
+    CSIM_REQUIRE(u->h == 1, CSIM_ERR_UNSUPPORTED, "csim_run_steps: needs halo == 1 (main.cpp:65)");
+    CSIM_REQUIRE(c->comm != nullptr, CSIM_ERR_COMM, "csim_run_steps: tile has neighbours but no communicator");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    StepK k;
+    int mode = 0;
+    if (int rc = step_setup(u, p, &k, &mode)) return rc;
+    // Blocking T steps needs T lines from every neighbour and a tile at least T cells wide (every
+    // rank's tile: the last rank of a dimension is never the smallest, decomp.cpp:29-30).
+    const int min_nx = dec->nx_global / dec->dims[0], min_ny = dec->ny_global / dec->dims[1];
+    int maxT = (mode == MODE_DIV || (p->flags & CSIM_STEP_NO_TEMPORAL)) ? 1 : tb_max_T();
+    if (maxT > min_nx) maxT = min_nx;
+    if (maxT > min_ny) maxT = min_ny;
+    if (maxT < 1 || (p->flags & CSIM_STEP_NO_TEMPORAL)) {
+        // reference-shaped path: one-line exchange, then one step, every step
+        for (int n = 0; n < nsteps; ++n) {
+            if (int rc = csim_halo_exchange(u, dec)) return rc;     // main.cpp:101
+            if (int rc = csim_step_fused(u, tmp, p, 1)) return rc;  // main.cpp:102-109
+        }
+        return CSIM_OK;
+    }
+    int left = nsteps;
+    while (left > 0) {
+        const int T = left < maxT ? left : maxT;
+        // main stream: the work items that read no ghost line.  Exchange stream: pack → NCCL →
+        // unpack, then the frame items (edge strips, first/last chunk), which do read them.
+        CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+        if (int rc = wide_exchange(u, dec, T, c->stream_x)) return rc;
+        bool launched = false;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched)) return rc;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched)) return rc;
+        CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        csim_field_swap(u, tmp);
+        left -= T;
     }
     return CSIM_OK;
 }

@@ -313,7 +313,10 @@ int launch_step_v1(const csim_field* u, csim_field* out, const StepK& k, bool us
 
 // ---- temporally blocked sweep (step_tb.cuh): host-side geometry and dispatch ---------------------
 
-static int tb_max_T() {
+// With fewer than 3 chunks (or no interior strip) there is nothing to overlap with the exchange.
+bool tb_split_pointless(int nchunks, int n_int) { return nchunks < 3 || n_int < 1; }
+
+int tb_max_T() {
     static int cached = -1;
     if (cached < 0) {
         cached = 3;  // T = 4 spills registers and measures slower (profiles/r01_tb_tuning.md)
@@ -330,9 +333,12 @@ static int tb_env_int(const char* name, int dflt) {
 }
 
 // Advance `u` by T steps into `out` in one sweep.  nbr/bc as in csim_step_params.  Sides with a
-// neighbour are read as they are in memory (one ghost line), so T must be 1 there.
+// neighbour must hold T valid ghost lines (csim::wide_exchange; T == 1: csim_halo_exchange).
+// part: TB_ALL, or TB_INTERIOR / TB_FRAME to split the sweep into the work items that do not / do
+// read ghost lines, so the former can run while the exchange is in flight.  Returns CSIM_OK and
+// sets *launched = false when the requested part is empty.
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T) {
+                   int T, int part, cudaStream_t stream, bool* launched) {
     csim_ctx* c = u->ctx;
     const int nx = u->nx, ny = u->ny;
     TbArgs a;
@@ -345,11 +351,11 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     for (int s = 0; s < 4; ++s)
         if (p->nbr[s] == CSIM_PROC_NULL) a.phys |= 1 << s;
     const bool pl = a.phys & 1, pr = a.phys & 2, pb = a.phys & 4, pt = a.phys & 8;
-    CSIM_REQUIRE(T == 1 || a.phys == 15, CSIM_ERR_INVALID, "launch_step_tb: T > 1 needs all sides physical");
-    a.xlo = 0;
-    a.xhi = nx;
-    a.ylo = 0;
-    a.yhi = ny;
+    if (launched) *launched = false;
+    a.xlo = pl ? 0 : -T;  // ghost lines of a neighbour side are advanced too (their validity shrinks
+    a.xhi = pr ? nx : nx + T;  // by one line per level, which is exactly what T lines allow)
+    a.ylo = pb ? 0 : -T;
+    a.yhi = pt ? ny : ny + T;
     a.sx0 = pl ? -1 : 0;
     a.sx1 = pr ? nx + 1 : nx;
     a.sy0 = pb ? -1 : 0;
@@ -391,20 +397,49 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.nchunks = (rows + ch - 1) / ch;
     const int eh = (ch + a.edge_split - 1) / a.edge_split;
     const int nch_edge = (rows + eh - 1) / eh;
+    a.int_chunk0 = 0;
+    a.frame_pair = 0;
+    int int_chunks = a.nchunks;
     a.n_edge_items = n_edge * nch_edge;
-    a.n_items = n_int * a.nchunks + a.n_edge_items;
+    if (part == TB_INTERIOR) {  // interior strips, all chunks but the first and the last
+        a.n_edge_items = 0;
+        a.int_chunk0 = 1;
+        int_chunks = a.nchunks - 2;
+    } else if (part == TB_FRAME) {  // both edge strips + first and last chunk of every interior strip
+        a.frame_pair = 1;
+        int_chunks = a.nchunks >= 2 ? 2 : a.nchunks;
+        if (tb_split_pointless(a.nchunks, n_int)) {  // the interior part is empty: the frame is everything
+            a.frame_pair = 0;
+            int_chunks = a.nchunks;
+        }
+    }
+    if (int_chunks < 0) int_chunks = 0;
+    a.n_items = n_int * int_chunks + a.n_edge_items;
+    if (a.n_items <= 0) return CSIM_OK;
+    if (launched) *launched = true;
     cudaError_t e;
     const bool vxp = k.vx_pos != 0, vyp = k.vy_pos != 0;
     if (vxp && vyp)
-        e = tb_launch_pp(T, mode, a, c->stream);
+        e = tb_launch_pp(T, mode, a, stream);
     else if (vxp)
-        e = tb_launch_pn(T, mode, a, c->stream);
+        e = tb_launch_pn(T, mode, a, stream);
     else if (vyp)
-        e = tb_launch_np(T, mode, a, c->stream);
+        e = tb_launch_np(T, mode, a, stream);
     else
-        e = tb_launch_nn(T, mode, a, c->stream);
+        e = tb_launch_nn(T, mode, a, stream);
     ++c->launches;
     if (e != cudaSuccess) return cuda_fail(e, "k_step_tb", __FILE__, __LINE__);
+    return CSIM_OK;
+}
+
+// physics constants and arithmetic mode of a step on tile `u`
+int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mode) {
+    for (int s = 0; s < 4; ++s)
+        CSIM_REQUIRE(p->bc[s] >= 0 && p->bc[s] <= 2, CSIM_ERR_INVALID, "step: unknown BC type");
+    bool use_div = false;
+    *k = make_consts(u->dx, u->dy, p->D, p->vx, p->vy, p->dt, p->flags, &use_div);
+    const bool unit = k->rdx2 == 1.0 && k->rdy2 == 1.0 && k->rdx == 1.0 && k->rdy == 1.0;
+    *mode = use_div ? MODE_DIV : (unit ? MODE_UNIT : MODE_RECIP);
     return CSIM_OK;
 }
 
@@ -480,10 +515,9 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     CSIM_REQUIRE(u->h == 1, CSIM_ERR_UNSUPPORTED, "csim_step_fused: the fused path needs halo == 1 (main.cpp:65)");
     csim_ctx* c = u->ctx;
     CSIM_CUDA(cudaSetDevice(c->device));
-    bool use_div = false;
-    const StepK k = make_consts(u->dx, u->dy, p->D, p->vx, p->vy, p->dt, p->flags, &use_div);
-    for (int s = 0; s < 4; ++s)
-        CSIM_REQUIRE(p->bc[s] >= 0 && p->bc[s] <= 2, CSIM_ERR_INVALID, "csim_step_fused: unknown BC type");
+    StepK k;
+    int mode = 0;
+    if (int rc = step_setup(u, p, &k, &mode)) return rc;
     if (u->nx == 0 || u->ny == 0) {  // nothing to advance; keep the reference's swap parity
         if (nsteps & 1) csim_field_swap(u, tmp);
         return CSIM_OK;
@@ -493,22 +527,21 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
         // cross-check of the blocked kernel)
         for (int n = 0; n < nsteps; ++n) {
             if (int rc = launch_boundary(u, p->nbr, p->bc, p->bc_value)) return rc;  // main.cpp:102
-            if (int rc = launch_step_v1(u, tmp, k, use_div)) return rc;              // main.cpp:104-107
+            if (int rc = launch_step_v1(u, tmp, k, mode == MODE_DIV)) return rc;     // main.cpp:104-107
             csim_field_swap(u, tmp);                                                 // main.cpp:109
         }
         return CSIM_OK;
     }
-    const bool unit = k.rdx2 == 1.0 && k.rdy2 == 1.0 && k.rdx == 1.0 && k.rdy == 1.0;
-    const int mode = use_div ? MODE_DIV : (unit ? MODE_UNIT : MODE_RECIP);
     bool all_phys = true;
     for (int s = 0; s < 4; ++s) all_phys = all_phys && p->nbr[s] == CSIM_PROC_NULL;
     // IEEE division is compute-bound: blocking in time buys nothing there.  Tiles with neighbours
-    // carry one ghost line per exchange, so they advance one step per sweep.
+    // carry one ghost line per csim_halo_exchange, so here they advance one step per sweep
+    // (csim_run_steps exchanges T lines and blocks them too).
     const int maxT = (mode == MODE_DIV || !all_phys) ? 1 : tb_max_T();
     int left = nsteps;
     while (left > 0) {
         const int T = left < maxT ? left : maxT;
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T)) return rc;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_ALL, c->stream, nullptr)) return rc;
         csim_field_swap(u, tmp);
         left -= T;
     }

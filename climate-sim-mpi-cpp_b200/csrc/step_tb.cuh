@@ -52,8 +52,10 @@ struct TbArgs {
     int nchunks;       // chunks down y for interior strips
     int chunk_h;       // rows per chunk (interior strips); edge strips use chunk_h / edge_split
     int edge_split;
-    int n_items;       // total (strip, chunk) work items
-    int n_edge_items;  // of which the first n_edge_items belong to the edge strips
+    int n_items;       // total (strip, chunk) work items of this launch
+    int n_edge_items;  // of which the first n_edge_items belong to the edge strips (0: none in this launch)
+    int int_chunk0;    // interior strips: first chunk enumerated ...
+    int frame_pair;    // ... or, if set, exactly the first and the last chunk of every interior strip
     int xmax_load;     // a lane may load its 4 cells iff x0+3 < xmax_load (row allocation bound)
     int pf_rows;       // L2 prefetch distance in rows (0 = off)
     int row_limit;     // rows y < row_limit are inside the allocation
@@ -269,7 +271,9 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
             const int e = item - a.n_edge_items;
             strip = 1 + e % n_int;
             h = a.chunk_h;
-            ya = a.sy0 + (e / n_int) * h;
+            const int ci = e / n_int;
+            const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
+            ya = a.sy0 + chunk * h;
         }
     }
     if (ya >= a.sy1) return;

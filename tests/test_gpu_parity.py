@@ -305,7 +305,7 @@ def test_minmax_and_health(csim, ctx):
 
 # ---- multi-GPU halo exchange (needs >= 2 devices; the 1-GPU box skips) ---------------------------
 
-def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, results, errors):
+def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors):
     try:
         c = csim.Context(rank)
         c.comm_init(size, rank, uid)
@@ -314,34 +314,51 @@ def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, results, erro
         u = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         tmp = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         u.upload(t0)
-        p = csim.make_step_params(*phys, csim.BCConfig(*[csim.BCType(b) for b in bc]), dec)
-        csim.run_steps(u, tmp, p, dec, steps)
+        p = csim.make_step_params(*phys, csim.BCConfig(*[csim.BCType(b) for b in bc]), dec, 0.0, flags)
+        for k in steps:  # several calls: the block structure must not leak across calls
+            csim.run_steps(u, tmp, p, dec, k)
         results[rank] = (dec, u.download_interior())
         c.sync()
     except Exception as e:  # noqa: BLE001
         errors.append((rank, repr(e)))
 
 
-def test_multi_gpu_halo_exchange_matches_single_rank_oracle(csim, oracle_mod, port):
+def _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=0):
     import threading
+    uid = csim.comm_unique_id()
+    results, errors = {}, []
+    th = [threading.Thread(target=_rank_worker, args=(csim, size, r, uid, nxg, nyg, steps, phys, bc, flags,
+                                                      results, errors)) for r in range(size)]
+    [t.start() for t in th]
+    [t.join(180) for t in th]
+    assert not errors, errors
+    assert len(results) == size, "a rank did not finish"
+    glob = np.zeros((nyg, nxg))
+    for dec, tile in results.values():
+        glob[dec.y_offset:dec.y_offset + dec.ny_local, dec.x_offset:dec.x_offset + dec.nx_local] = tile
+    return glob
 
+
+def test_multi_gpu_matches_single_rank_oracle(csim, oracle_mod, port):
+    """Ranks = GPUs of one box (threads here, processes under torchrun).  By decomposition
+    invariance the single-rank oracle pins every decomposition.  Covers: the blocked path with the
+    wide (T-line, 8-neighbour) exchange overlapped with the interior sweep, the reference-shaped
+    one-line exchange (CSIM_STEP_NO_TEMPORAL), tiles with remainders, tiles too small to split."""
     import torch
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs")
+    cases = [  # (nxg, nyg, step chunks, physics, bc)
+        (203, 150, (25,), (0.05, -0.5, 0.3, 0.1), (0, 1, 2, 0)),
+        (1000, 700, (7, 3, 1, 5), (0.05, 0.5, -0.3, 0.1), (2, 2, 2, 2)),
+        (777, 1301, (10,), (0.05, -0.4, -0.2, 0.1), (1, 0, 1, 2)),
+    ]
     for size in [s for s in (2, 4, 8) if s <= ngpu]:
-        nxg, nyg, steps = 203, 150, 25  # remainders on purpose
-        phys, bc = (0.05, -0.5, 0.3, 0.1), (0, 1, 2, 0)
-        uid = csim.comm_unique_id()
-        results, errors = {}, []
-        th = [threading.Thread(target=_rank_worker, args=(csim, size, r, uid, nxg, nyg, steps, phys, bc,
-                                                          results, errors)) for r in range(size)]
-        [t.start() for t in th]
-        [t.join(120) for t in th]
-        assert not errors, errors
-        glob = np.zeros((nyg, nxg))
-        for dec, tile in results.values():
-            glob[dec.y_offset:dec.y_offset + dec.ny_local, dec.x_offset:dec.x_offset + dec.nx_local] = tile
-        sp = oracle_mod.SimParams(nx=nxg, ny=nyg, D=phys[0], vx=phys[1], vy=phys[2], dt=phys[3], steps=steps,
-                                  out_every=steps, bc=bc)
-        assert bits_equal(glob, port.run(sp)["final"]), size
+        for (nxg, nyg, steps, phys, bc) in cases:
+            sp = oracle_mod.SimParams(nx=nxg, ny=nyg, D=phys[0], vx=phys[1], vy=phys[2], dt=phys[3],
+                                      steps=sum(steps), out_every=sum(steps), bc=bc)
+            want = port.run(sp)["final"]
+            got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc)
+            assert bits_equal(got, want), ("blocked", size, nxg, nyg)
+            got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=csim.STEP_NO_TEMPORAL)
+            assert bits_equal(got, want), ("one-line", size, nxg, nyg)
