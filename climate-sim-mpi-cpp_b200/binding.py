@@ -81,6 +81,11 @@ STEP_FAST_RECIP = 0x1
 STEP_NO_TEMPORAL = 0x2
 
 
+class XRegion(C.Structure):
+    """csim_xregion"""
+    _fields_ = [("x0", C.c_int), ("y0", C.c_int), ("w", C.c_int), ("h", C.c_int), ("peer", C.c_int)]
+
+
 class _Decomp(C.Structure):
     _fields_ = [("dims", C.c_int * 2), ("coords", C.c_int * 2), ("nbr", C.c_int * 4),
                 ("nx_global", C.c_int), ("ny_global", C.c_int), ("nx_local", C.c_int),
@@ -128,7 +133,9 @@ def lib():
             "csim_comm_unique_id": [C.c_char_p],
             "csim_comm_init": [vp, C.c_int, C.c_int, C.c_char_p],
             "csim_comm_destroy": [vp],
+            "csim_comm_allreduce_max": [vp, dp, C.c_int],
             "csim_halo_exchange": [vp, C.POINTER(_Decomp)],
+            "csim_wide_exchange_plan": [C.POINTER(_Decomp), C.c_int, C.POINTER(XRegion), C.POINTER(XRegion)],
             "csim_run_steps": [vp, vp, C.POINTER(StepParams), C.POINTER(_Decomp), C.c_int],
             "csim_initial_condition_host": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int,
                                             C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
@@ -201,6 +208,12 @@ class Context:
     def comm_init(self, size: int, rank: int, unique_id: bytes):
         assert len(unique_id) == UNIQUE_ID_BYTES
         _check(lib().csim_comm_init(self._h, size, rank, unique_id))
+
+    def allreduce_max(self, values):
+        """MPI_Reduce(MAX) over the ranks of this context's communicator (all ranks get the result)."""
+        arr = (C.c_double * len(values))(*values)
+        _check(lib().csim_comm_allreduce_max(self._h, arr, len(values)))
+        return list(arr)
 
     def close(self):
         if self._h:
@@ -366,6 +379,13 @@ def apply_boundary(f: Field, dec, bc: BCConfig, value: float = 0.0):
 def exchange_halos(f: Field, dec: Decomp2D):
     """include/halo.hpp:7 (the communicator is the one bound to the field's context)"""
     _check(lib().csim_halo_exchange(f._h, C.byref(dec._c)))
+
+
+def wide_exchange_plan(dec: Decomp2D, T: int):
+    """(send, recv) lists of 8 XRegion each: the geometry of the T-line exchange of csim_run_steps."""
+    snd, rcv = (XRegion * 8)(), (XRegion * 8)()
+    _check(lib().csim_wide_exchange_plan(C.byref(dec._c), T, snd, rcv))
+    return list(snd), list(rcv)
 
 
 def safe_dt(dx, dy, vx, vy, D) -> float:

@@ -28,6 +28,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -54,6 +56,7 @@ static int load_nccl() {
     CSIM_SYM(CommDestroy, "ncclCommDestroy");
     CSIM_SYM(Send, "ncclSend");
     CSIM_SYM(Recv, "ncclRecv");
+    CSIM_SYM(AllReduce, "ncclAllReduce");
     CSIM_SYM(GroupStart, "ncclGroupStart");
     CSIM_SYM(GroupEnd, "ncclGroupEnd");
     CSIM_SYM(GetErrorString, "ncclGetErrorString");
@@ -129,40 +132,18 @@ __global__ void __launch_bounds__(256) k_unpack_regions(double* __restrict__ u, 
 // Fill T ghost lines of `f` on every side that has a neighbour, on `stream`.
 static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream) {
     csim_ctx* c = f->ctx;
-    const int nx = f->nx, ny = f->ny;
-    const int cx = dec->coords[0], cy = dec->coords[1];
-    auto rank_of = [&](int x, int y) {
-        return (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) ? -1 : x * dec->dims[1] + y;
-    };
-    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pr = dec->nbr[CSIM_RIGHT] == CSIM_PROC_NULL;
-    const bool pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL, pt = dec->nbr[CSIM_TOP] == CSIM_PROC_NULL;
-    // extent of a band along its own side: interior plus the ghost line of a physical end
-    const int bx0 = pl ? -1 : 0, bx1 = pr ? nx + 1 : nx;
-    const int by0 = pb ? -1 : 0, by1 = pt ? ny + 1 : ny;
+    csim_decomp d = *dec;  // the plan is a function of the decomposition; the tile fixes the local size
+    d.nx_local = f->nx;
+    d.ny_local = f->ny;
+    csim_xregion ps[8], pr8[8];
+    if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
     XTable snd, rcv;
     long long off = 0;
-    int k = 0;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (dx == 0 && dy == 0) continue;
-            XRegion s, r;
-            s.peer = r.peer = rank_of(cx + dx, cy + dy);
-            // what I send towards (dx,dy): my own cells next to that side
-            s.x0 = dx < 0 ? 0 : (dx > 0 ? nx - T : bx0);
-            s.w = dx != 0 ? T : bx1 - bx0;
-            s.y0 = dy < 0 ? 0 : (dy > 0 ? ny - T : by0);
-            s.h = dy != 0 ? T : by1 - by0;
-            // where what comes from (dx,dy) lands: my ghost area on that side
-            r.x0 = dx < 0 ? -T : (dx > 0 ? nx : bx0);
-            r.w = s.w;
-            r.y0 = dy < 0 ? -T : (dy > 0 ? ny : by0);
-            r.h = s.h;
-            s.off = off;
-            off += static_cast<long long>(s.w) * s.h;
-            snd.r[k] = s;
-            rcv.r[k] = r;
-            ++k;
-        }
+    for (int q = 0; q < 8; ++q) {
+        snd.r[q] = XRegion{ps[q].x0, ps[q].y0, ps[q].w, ps[q].h, off, ps[q].peer};
+        rcv.r[q] = XRegion{pr8[q].x0, pr8[q].y0, pr8[q].w, pr8[q].h, 0, pr8[q].peer};
+        off += static_cast<long long>(ps[q].w) * ps[q].h;
+    }
     const long long send_total = off;
     for (int q = 0; q < 8; ++q) rcv.r[q].off = send_total + snd.r[q].off;
     if (c->wide_doubles < static_cast<size_t>(2 * send_total)) {
@@ -235,6 +216,29 @@ int csim_comm_destroy(csim_ctx* c) {
         g_nccl.CommDestroy(static_cast<ncclComm_t>(c->comm));
         c->comm = nullptr;
     }
+    return CSIM_OK;
+}
+
+int csim_comm_allreduce_max(csim_ctx* c, double* inout, int n) {
+    CSIM_REQUIRE(c != nullptr && n >= 0 && (n == 0 || inout != nullptr), CSIM_ERR_INVALID,
+                 "csim_comm_allreduce_max: bad arguments");
+    CSIM_REQUIRE(static_cast<size_t>(n) + 1 <= c->scratch_doubles, CSIM_ERR_INVALID,
+                 "csim_comm_allreduce_max: too many elements");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    if (!c->comm) {
+        CSIM_CUDA(cudaStreamSynchronize(c->stream));
+        return CSIM_OK;
+    }
+    const size_t cnt = static_cast<size_t>(n) + 1;  // one dummy element so that n == 0 is a barrier
+    for (int k = 0; k < n; ++k) c->h_scratch[k] = inout[k];
+    c->h_scratch[n] = 0.0;
+    CSIM_CUDA(cudaMemcpyAsync(c->d_scratch, c->h_scratch, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CSIM_NCCL(g_nccl.AllReduce(c->d_scratch, c->d_scratch, cnt, ncclDouble, ncclMax, static_cast<ncclComm_t>(c->comm),
+                               c->stream));
+    ++c->launches;
+    CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, c->d_scratch, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; ++k) inout[k] = c->h_scratch[k];
     return CSIM_OK;
 }
 

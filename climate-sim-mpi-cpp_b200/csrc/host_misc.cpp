@@ -54,6 +54,44 @@ int csim_decomp_init(int size, int rank, int nxg, int nyg, csim_decomp* d) {
     return CSIM_OK;
 }
 
+// Geometry of the wide exchange (used by halo.cu and, on the CPU, by the gloo tests).
+int csim_wide_exchange_plan(const csim_decomp* dec, int T, csim_xregion snd[8], csim_xregion rcv[8]) {
+    CSIM_REQUIRE(dec != nullptr && snd != nullptr && rcv != nullptr, CSIM_ERR_INVALID,
+                 "csim_wide_exchange_plan: null argument");
+    CSIM_REQUIRE(T >= 1 && T <= kMaxHalo, CSIM_ERR_INVALID, "csim_wide_exchange_plan: T out of range");
+    const int nx = dec->nx_local, ny = dec->ny_local;
+    const int cx = dec->coords[0], cy = dec->coords[1];
+    auto rank_of = [&](int x, int y) {
+        return (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) ? -1 : x * dec->dims[1] + y;
+    };
+    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pr = dec->nbr[CSIM_RIGHT] == CSIM_PROC_NULL;
+    const bool pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL, pt = dec->nbr[CSIM_TOP] == CSIM_PROC_NULL;
+    // extent of a band along its own side: interior plus the ghost line of a physical end
+    const int bx0 = pl ? -1 : 0, bx1 = pr ? nx + 1 : nx;
+    const int by0 = pb ? -1 : 0, by1 = pt ? ny + 1 : ny;
+    int k = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            csim_xregion s, r;
+            s.peer = r.peer = rank_of(cx + dx, cy + dy);
+            // what goes towards (dx,dy): own cells next to that side
+            s.x0 = dx < 0 ? 0 : (dx > 0 ? nx - T : bx0);
+            s.w = dx != 0 ? T : bx1 - bx0;
+            s.y0 = dy < 0 ? 0 : (dy > 0 ? ny - T : by0);
+            s.h = dy != 0 ? T : by1 - by0;
+            // where what comes from (dx,dy) lands: the ghost area on that side
+            r.x0 = dx < 0 ? -T : (dx > 0 ? nx : bx0);
+            r.w = s.w;
+            r.y0 = dy < 0 ? -T : (dy > 0 ? ny : by0);
+            r.h = s.h;
+            snd[k] = s;
+            rcv[k] = r;
+            ++k;
+        }
+    return CSIM_OK;
+}
+
 // apply_initial_condition — src/init.cpp:12-47.  Host libm exp() keeps the tile bit-identical to
 // the reference's; rows are split over host threads (each cell is independent).
 int csim_initial_condition_host(double* host, const csim_decomp* dec, int halo, int nxg, int nyg, double dx,

@@ -195,12 +195,28 @@ int csim_decomp_init(int size, int rank, int nx_global, int ny_global, csim_deco
 int csim_comm_unique_id(char id[CSIM_UNIQUE_ID_BYTES]);
 int csim_comm_init(csim_ctx* ctx, int size, int rank, const char id[CSIM_UNIQUE_ID_BYTES]);
 int csim_comm_destroy(csim_ctx* ctx);
+/* MPI_Reduce(..., MPI_DOUBLE, MPI_MAX, 0, comm) of src/main.cpp:127-128 (every rank gets the
+ * result) and, with n == 0, MPI_Barrier (main.cpp:82): element-wise max of `n` host doubles over
+ * all ranks of the context's communicator; synchronous.  Without a communicator it is the identity. */
+int csim_comm_allreduce_max(csim_ctx* ctx, double* inout, int n);
 
 /* exchange_halos(Field&, const Decomp2D&, MPI_Comm): fill the ghost lines of `f` from the up to
  * four neighbours in `dec->nbr`: columns over j in [h, h+ny), rows over all nx+2h cells
  * (src/halo.cpp:28-43).  Edge lines are packed by a kernel, moved with grouped ncclSend/ncclRecv
  * over NVLink, and unpacked by a kernel; all on the context stream. */
 int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
+
+/* One region of the wide (T-line, 8-neighbour) exchange csim_run_steps performs per T-step block:
+ * interior coordinates of its first cell, extent, and the rank on the other side (-1: no such
+ * neighbour).  Index k enumerates directions (dx,dy) row by row from (-1,-1) to (1,1) without (0,0). */
+typedef struct csim_xregion {
+    int x0, y0, w, h;
+    int peer;
+} csim_xregion;
+/* Host-only: the regions a rank with decomposition `dec` packs (send[k], out of its own tile) and
+ * fills (recv[k], in its ghost area) when exchanging T lines.  Bands span the ghost line of a
+ * perpendicular physical side (frozen "periodic" ghosts travel with them); corners are T x T. */
+int csim_wide_exchange_plan(const csim_decomp* dec, int T, csim_xregion send[8], csim_xregion recv[8]);
 
 /* ---- the loop ------------------------------------------------------------------------------ */
 

@@ -362,3 +362,17 @@ def test_multi_gpu_matches_single_rank_oracle(csim, oracle_mod, port):
             assert bits_equal(got, want), ("blocked", size, nxg, nyg)
             got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=csim.STEP_NO_TEMPORAL)
             assert bits_equal(got, want), ("one-line", size, nxg, nyg)
+
+
+# ---- the C++ drop-in layer (host/): the reference's unit tests restated in C++ --------------------
+
+def test_cpp_dropin_unit_tests():
+    """host/tests/test_dropin.cpp: Field / diffusion / advection / boundary / stability / decomp tests
+    of the reference, written against the drop-in headers, plus main.cpp's loop body vs the fused path."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "climate-sim-mpi-cpp_b200", "host", "build", "test_dropin")
+    assert os.path.exists(exe), "host/build/test_dropin missing: run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
