@@ -154,6 +154,7 @@ def lib():
         L.csim_safe_dt.argtypes = [C.c_double] * 5
         L.csim_safe_dt.restype = C.c_double
         L.csim_abi_version.restype = C.c_int
+        L.csim_steps_per_sweep.restype = C.c_int
         _lib = L
     return _lib
 
@@ -379,6 +380,11 @@ def apply_boundary(f: Field, dec, bc: BCConfig, value: float = 0.0):
 def exchange_halos(f: Field, dec: Decomp2D):
     """include/halo.hpp:7 (the communicator is the one bound to the field's context)"""
     _check(lib().csim_halo_exchange(f._h, C.byref(dec._c)))
+
+
+def steps_per_sweep() -> int:
+    """Temporal blocking depth T of the fused sweep."""
+    return lib().csim_steps_per_sweep()
 
 
 def wide_exchange_plan(dec: Decomp2D, T: int):

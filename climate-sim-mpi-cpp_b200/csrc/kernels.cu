@@ -548,6 +548,8 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     return CSIM_OK;
 }
 
+int csim_steps_per_sweep(void) { return tb_max_T(); }
+
 int csim_minmax(const csim_field* f, double* mn, double* mx) {
     CSIM_REQUIRE(f != nullptr && mn != nullptr && mx != nullptr, CSIM_ERR_INVALID, "csim_minmax: null argument");
     CSIM_REQUIRE(f->nxt() > 0 && f->nyt() > 0, CSIM_ERR_INVALID, "csim_minmax: empty field");

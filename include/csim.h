@@ -162,6 +162,8 @@ typedef struct csim_step_params {
  * Sides with a neighbour (nbr != PROC_NULL) read their ghost line as the exchange left it, so
  * for multi-rank runs call csim_halo_exchange before each step (or use csim_run_steps). */
 int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, int nsteps);
+/* Largest number of time steps one sweep advances (the temporal blocking depth T; env CSIM_TB_MAXT). */
+int csim_steps_per_sweep(void);
 
 /* min / max over the whole padded tile, ghosts included — the "IC min/max" reduction of
  * src/main.cpp:73-77 (std::min_element / std::max_element over Field::data). */
