@@ -135,6 +135,8 @@ def lib():
             "csim_comm_destroy": [vp],
             "csim_comm_allreduce_max": [vp, dp, C.c_int],
             "csim_halo_exchange": [vp, C.POINTER(_Decomp)],
+            "csim_peer_setup": [vp, vp, C.POINTER(_Decomp)],
+            "csim_peer_teardown": [vp],
             "csim_wide_exchange_plan": [C.POINTER(_Decomp), C.c_int, C.POINTER(XRegion), C.POINTER(XRegion)],
             "csim_run_steps": [vp, vp, C.POINTER(StepParams), C.POINTER(_Decomp), C.c_int],
             "csim_initial_condition_host": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int,
@@ -392,6 +394,16 @@ def wide_exchange_plan(dec: Decomp2D, T: int):
     snd, rcv = (XRegion * 8)(), (XRegion * 8)()
     _check(lib().csim_wide_exchange_plan(C.byref(dec._c), T, snd, rcv))
     return list(snd), list(rcv)
+
+
+def peer_setup(u: Field, tmp: Field, dec: Decomp2D):
+    """Collective: map the neighbours' tiles (CUDA IPC / peer access) so run_steps pushes halos
+    directly into their ghost lines instead of going through NCCL."""
+    _check(lib().csim_peer_setup(u._h, tmp._h, C.byref(dec._c)))
+
+
+def peer_teardown(ctx: Context):
+    _check(lib().csim_peer_teardown(ctx._h))
 
 
 def safe_dt(dx, dy, vx, vy, D) -> float:

@@ -74,6 +74,7 @@ int csim_ctx_create(int device, csim_ctx** out) {
     }
     CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming));
     c->scratch_doubles = 4096;
     CSIM_CUDA(cudaMalloc(&c->d_scratch, c->scratch_doubles * sizeof(double)));
     CSIM_CUDA(cudaMallocHost(&c->h_scratch, c->scratch_doubles * sizeof(double)));
@@ -84,6 +85,7 @@ int csim_ctx_create(int device, csim_ctx** out) {
 int csim_ctx_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
+    csim_peer_teardown(c);
     if (c->comm) csim_comm_destroy(c);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
@@ -97,6 +99,7 @@ int csim_ctx_destroy(csim_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_go) cudaEventDestroy(c->ev_go);
     if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_wide) cudaFree(c->d_wide);
     delete c;
@@ -108,6 +111,8 @@ int csim_sync(csim_ctx* c) {
     CSIM_CUDA(cudaSetDevice(c->device));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    if (c->h_err && *c->h_err)
+        return fail(CSIM_ERR_TIMEOUT, "csim_sync: a neighbour's halo did not arrive within the bounded wait");
     return CSIM_OK;
 }
 
@@ -154,6 +159,11 @@ int csim_field_destroy(csim_field* f) {
     if (!f) return CSIM_OK;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
+    cudaStreamSynchronize(f->ctx->stream_x);
+    // a tile that is mapped by the neighbours takes the peer links down with it: a later tile may
+    // get the same address, and pushing through stale mappings would corrupt the neighbours
+    if (f->ctx->peer_ready && (f->base == f->ctx->peer_tile[0] || f->base == f->ctx->peer_tile[1]))
+        csim_peer_teardown(f->ctx);
     if (f->base) cudaFree(f->base);
     delete f;
     return CSIM_OK;

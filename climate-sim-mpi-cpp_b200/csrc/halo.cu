@@ -14,8 +14,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "csim_internal.hpp"
 #include "step_tb.cuh"
@@ -30,6 +33,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -57,6 +61,7 @@ static int load_nccl() {
     CSIM_SYM(Send, "ncclSend");
     CSIM_SYM(Recv, "ncclRecv");
     CSIM_SYM(AllReduce, "ncclAllReduce");
+    CSIM_SYM(AllGather, "ncclAllGather");
     CSIM_SYM(GroupStart, "ncclGroupStart");
     CSIM_SYM(GroupEnd, "ncclGroupEnd");
     CSIM_SYM(GetErrorString, "ncclGetErrorString");
@@ -176,6 +181,132 @@ static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     return CSIM_OK;
 }
 
+// ---- peer-memory exchange: store the bands straight into the neighbours' ghost lines ---------------
+struct PushRegion {
+    int x0, y0, w, h;     // source region in this rank's tile (interior coordinates)
+    double* dst;          // neighbour's cell that receives the region's first cell (mapped pointer)
+    long long dst_pitch;  // neighbour's row pitch
+    unsigned* flag;       // neighbour's flag word for this direction, nullptr: no neighbour
+};
+struct PushTable {
+    PushRegion r[8];
+};
+
+// Copy all regions, then (last CTA only, after a system-scope fence) publish `seq` in every
+// neighbour's flag word.  Few small CTAs on purpose: the kernel has to find SM slots while the
+// interior sweep fills the machine.
+__global__ void __launch_bounds__(128) k_push_regions(const double* __restrict__ u, long long pitch, PushTable t,
+                                                      unsigned seq, unsigned* __restrict__ ticket) {
+    for (int q = 0; q < 8; ++q) {
+        const PushRegion g = t.r[q];
+        if (!g.flag) continue;
+        const int n = g.w * g.h;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+            const int yy = e / g.w, xx = e - yy * g.w;
+            g.dst[static_cast<long long>(yy) * g.dst_pitch + xx] =
+                u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx];
+        }
+    }
+    __threadfence_system();  // this thread's peer stores are visible system-wide before the ticket
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 8) {
+        if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next push (stream order protects it)
+        unsigned* f = t.r[threadIdx.x].flag;
+        if (f) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(f) = seq;
+        }
+    }
+}
+
+// Gate of the frame sweep: wait until every neighbour in `mask` has published >= seq.  Bounded: after
+// `timeout_ns` the kernel records the failure and returns, so a lost neighbour ends in an error code.
+__global__ void k_wait_flags(const unsigned* flags, unsigned mask, unsigned seq, unsigned long long timeout_ns,
+                             unsigned* err) {
+    const int k = threadIdx.x;
+    if (k >= 8 || !((mask >> k) & 1)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const volatile unsigned* f = flags + k;
+    // seq wraps after 2^32 exchanges; compare as a signed distance
+    while (static_cast<int>(*f - seq) < 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicExch(err, 1u + static_cast<unsigned>(k));
+            return;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+static bool peer_path_enabled(const csim_ctx* c, const csim_field* u, const csim_field* tmp) {
+    if (!c->peer_ready) return false;
+    static const bool force_nccl = [] {
+        const char* e = std::getenv("CSIM_HALO");
+        return e && std::strcmp(e, "nccl") == 0;
+    }();
+    if (force_nccl) return false;
+    return (u->base == c->peer_tile[0] && tmp->base == c->peer_tile[1]) ||
+           (u->base == c->peer_tile[1] && tmp->base == c->peer_tile[0]);
+}
+
+// Peer version of wide_exchange: push this rank's bands of tile `f` into the neighbours' copy of
+// the same tile, then gate `stream` on the neighbours' pushes into ours.
+static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream) {
+    csim_ctx* c = f->ctx;
+    csim_decomp d = *dec;
+    d.nx_local = f->nx;
+    d.ny_local = f->ny;
+    csim_xregion ps[8], pr8[8];
+    if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
+    const int slot = f->base == c->peer_tile[0] ? 0 : 1;
+    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL;
+    PushTable t;
+    unsigned mask = 0;
+    int q = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            PushRegion& g = t.r[q];
+            g.x0 = ps[q].x0;
+            g.y0 = ps[q].y0;
+            g.w = ps[q].w;
+            g.h = ps[q].h;
+            g.dst = nullptr;
+            g.dst_pitch = 0;
+            g.flag = nullptr;
+            const csim_ctx::PeerLink& L = c->peer[q];
+            if (ps[q].peer >= 0) {
+                CSIM_REQUIRE(L.rank == ps[q].peer && L.tile[slot] != nullptr, CSIM_ERR_COMM,
+                             "peer_exchange: neighbour not mapped (csim_peer_setup with other tiles?)");
+                // my region lands in the neighbour's ghost area on ITS side (-dx,-dy): its own
+                // receive rule with its own tile size (bands keep their along-side origin: the
+                // neighbour shares that physical side with me)
+                const int rx = dx > 0 ? -T : (dx < 0 ? L.nx : (pl ? -1 : 0));
+                const int ry = dy > 0 ? -T : (dy < 0 ? L.ny : (pb ? -1 : 0));
+                double* interior = L.tile[slot] + static_cast<long long>(kLeadY) * L.pitch + kLeadX;
+                g.dst = interior + static_cast<long long>(ry) * L.pitch + rx;
+                g.dst_pitch = L.pitch;
+                g.flag = L.flags + (7 - q);  // the slot of direction (-dx,-dy) in the neighbour's array
+                mask |= 1u << q;
+            }
+            ++q;
+        }
+    const unsigned seq = ++c->push_seq;
+    k_push_regions<<<8, 128, 0, stream>>>(f->interior(), f->pitch, t, seq, c->d_flags + 8);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    k_wait_flags<<<1, 32, 0, stream>>>(c->d_flags, mask, seq, 5000000000ull, c->d_err);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    return CSIM_OK;
+}
+
 }  // namespace csim
 
 using namespace csim;
@@ -239,6 +370,131 @@ int csim_comm_allreduce_max(csim_ctx* c, double* inout, int n) {
     CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, c->d_scratch, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < n; ++k) inout[k] = c->h_scratch[k];
+    return CSIM_OK;
+}
+
+// Bootstrap record every rank contributes to the all-gather in csim_peer_setup.
+struct PeerInfo {
+    cudaIpcMemHandle_t tile[2];
+    cudaIpcMemHandle_t flags;
+    unsigned long long raw_tile[2], raw_flags;  // same-process pointers
+    long long pid;
+    long long pitch;
+    int nx, ny, device, pad;
+};
+
+int csim_peer_teardown(csim_ctx* c) {
+    CSIM_REQUIRE(c != nullptr, CSIM_ERR_INVALID, "csim_peer_teardown: ctx is null");
+    if (!c->peer_ready && !c->d_flags) return CSIM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream_x);
+    for (auto& L : c->peer) {
+        if (L.ipc) {
+            for (double*& t : L.tile)
+                if (t) cudaIpcCloseMemHandle(t);
+            if (L.flags) cudaIpcCloseMemHandle(L.flags);
+        }
+        L = csim_ctx::PeerLink();
+    }
+    c->peer_ready = false;
+    if (c->d_flags) cudaFree(c->d_flags);
+    c->d_flags = nullptr;
+    if (c->h_err) cudaFreeHost(c->h_err);
+    c->h_err = nullptr;
+    c->d_err = nullptr;
+    return CSIM_OK;
+}
+
+int csim_peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec) {
+    CSIM_REQUIRE(u != nullptr && tmp != nullptr && dec != nullptr, CSIM_ERR_INVALID, "csim_peer_setup: null argument");
+    csim_ctx* c = u->ctx;
+    CSIM_REQUIRE(c == tmp->ctx && u->pitch == tmp->pitch && u->nx == tmp->nx && u->ny == tmp->ny, CSIM_ERR_INVALID,
+                 "csim_peer_setup: tiles differ in geometry");
+    CSIM_REQUIRE(c->comm != nullptr, CSIM_ERR_COMM, "csim_peer_setup: needs csim_comm_init first");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    if (int rc = csim_peer_teardown(c)) return rc;
+    const int size = c->comm_size, me = c->comm_rank;
+    CSIM_CUDA(cudaMalloc(&c->d_flags, 16 * sizeof(unsigned)));
+    CSIM_CUDA(cudaMemset(c->d_flags, 0, 16 * sizeof(unsigned)));
+    CSIM_CUDA(cudaHostAlloc(&c->h_err, sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_err = 0;
+    CSIM_CUDA(cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
+    c->push_seq = 0;
+    c->peer_tile[0] = u->base;
+    c->peer_tile[1] = tmp->base;
+
+    PeerInfo mine;
+    std::memset(&mine, 0, sizeof mine);
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[0], u->base));
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[1], tmp->base));
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.flags, c->d_flags));
+    mine.raw_tile[0] = reinterpret_cast<unsigned long long>(u->base);
+    mine.raw_tile[1] = reinterpret_cast<unsigned long long>(tmp->base);
+    mine.raw_flags = reinterpret_cast<unsigned long long>(c->d_flags);
+    mine.pid = static_cast<long long>(getpid());
+    mine.pitch = u->pitch;
+    mine.nx = u->nx;
+    mine.ny = u->ny;
+    mine.device = c->device;
+
+    // all-gather of the records over the communicator that is already there
+    static_assert(sizeof(PeerInfo) % 8 == 0, "PeerInfo must be a whole number of doubles");
+    const size_t words = sizeof(PeerInfo) / 8;
+    double* d_all = nullptr;
+    CSIM_CUDA(cudaMalloc(&d_all, sizeof(PeerInfo) * static_cast<size_t>(size + 1)));
+    CSIM_CUDA(cudaMemcpyAsync(d_all + words * size, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    CSIM_NCCL(g_nccl.AllGather(d_all + words * size, d_all, words, ncclDouble, static_cast<ncclComm_t>(c->comm),
+                               c->stream));
+    std::vector<PeerInfo> all(static_cast<size_t>(size));
+    CSIM_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * static_cast<size_t>(size), cudaMemcpyDeviceToHost,
+                              c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaFree(d_all));
+
+    const int cx = dec->coords[0], cy = dec->coords[1];
+    int q = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            csim_ctx::PeerLink& L = c->peer[q++];
+            const int x = cx + dx, y = cy + dy;
+            if (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) continue;
+            const int r = x * dec->dims[1] + y;
+            CSIM_REQUIRE(r != me && r < size, CSIM_ERR_INVALID, "csim_peer_setup: bad neighbour rank");
+            const PeerInfo& o = all[static_cast<size_t>(r)];
+            L.rank = r;
+            L.pitch = o.pitch;
+            L.nx = o.nx;
+            L.ny = o.ny;
+            if (o.pid == mine.pid) {  // ranks are threads of one process: plain peer access
+                if (o.device != c->device) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(o.device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled)
+                        cudaGetLastError();
+                    else if (e != cudaSuccess)
+                        return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                }
+                L.tile[0] = reinterpret_cast<double*>(o.raw_tile[0]);
+                L.tile[1] = reinterpret_cast<double*>(o.raw_tile[1]);
+                L.flags = reinterpret_cast<unsigned*>(o.raw_flags);
+                L.ipc = false;
+            } else {
+                void* p0 = nullptr;
+                void* p1 = nullptr;
+                void* pf = nullptr;
+                CSIM_CUDA(cudaIpcOpenMemHandle(&p0, o.tile[0], cudaIpcMemLazyEnablePeerAccess));
+                CSIM_CUDA(cudaIpcOpenMemHandle(&p1, o.tile[1], cudaIpcMemLazyEnablePeerAccess));
+                CSIM_CUDA(cudaIpcOpenMemHandle(&pf, o.flags, cudaIpcMemLazyEnablePeerAccess));
+                L.tile[0] = static_cast<double*>(p0);
+                L.tile[1] = static_cast<double*>(p1);
+                L.flags = static_cast<unsigned*>(pf);
+                L.ipc = true;
+            }
+        }
+    // nobody pushes before everyone has mapped everyone (and zeroed its flags)
+    if (int rc = csim_comm_allreduce_max(c, nullptr, 0)) return rc;
+    c->peer_ready = true;
     return CSIM_OK;
 }
 
@@ -331,22 +587,50 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
         }
         return CSIM_OK;
     }
+    // Software pipeline over blocks of T steps, two streams:
+    //   exchange stream (high priority): go(n) → frame(n) → exchange(n+1)
+    //   main stream                    : wait go(n) → interior(n)
+    // frame(n) = the work items that read ghost lines (edge strips, first/last chunk of every strip);
+    // interior(n) = all the others.  The bands exchange(n+1) packs are all produced by frame(n), so
+    // the next block's halos travel while interior(n) runs and are in place when block n+1 starts.
+    //   frame(n)    needs exchange(n) (same stream) and interior(n-1) (event ev_fork)
+    //   interior(n) needs frame(n-1) and interior(n-1); it is released by the event go(n), recorded
+    //               on the exchange stream right before frame(n), so that both kernels become
+    //               eligible together and the high-priority frame blocks are placed first.  Released
+    //               by stream order alone, the interior blocks fill every SM a few microseconds
+    //               before the frame's event arrives and the frame waits a whole round for slots:
+    //               measured chain frame-wait 88 + frame 88 + exchange 132 us = 308 us per block
+    //               against 285 us of work (profiles/r01_multigpu_phases.md).
+    const bool p2p = peer_path_enabled(c, u, tmp);
+    if (p2p && *c->h_err)
+        return fail(CSIM_ERR_TIMEOUT, "csim_run_steps: a neighbour's halo did not arrive within the bounded wait");
+    auto exchange = [&](csim_field* f, int lines) {
+        return p2p ? peer_exchange(f, dec, lines, c->stream_x) : wide_exchange(f, dec, lines, c->stream_x);
+    };
     int left = nsteps;
+    int T = left < maxT ? left : maxT;
+    CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // everything queued so far = "interior(-1)"
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+    if (int rc = exchange(u, T)) return rc;  // exchange(0): the only one not hidden
+    bool first = true;
     while (left > 0) {
-        const int T = left < maxT ? left : maxT;
-        // main stream: the work items that read no ghost line.  Exchange stream: pack → NCCL →
-        // unpack, then the frame items (edge strips, first/last chunk), which do read them.
-        CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-        CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
-        if (int rc = wide_exchange(u, dec, T, c->stream_x)) return rc;
         bool launched = false;
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched)) return rc;
+        if (!first) CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));  // interior(n-1) done
+        CSIM_CUDA(cudaEventRecord(c->ev_go, c->stream_x));                       // go(n)
         if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched)) return rc;
-        CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));
-        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));                     // frame(n) done
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_go, 0));
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched)) return rc;
+        CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));                       // interior(n) done
         csim_field_swap(u, tmp);
         left -= T;
+        first = false;
+        if (left > 0) {
+            T = left < maxT ? left : maxT;
+            if (int rc = exchange(u, T)) return rc;  // exchange(n+1): reads frame(n)'s cells
+        }
     }
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the main stream orders everything again
     return CSIM_OK;
 }
 

@@ -538,10 +538,22 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     // carry one ghost line per csim_halo_exchange, so here they advance one step per sweep
     // (csim_run_steps exchanges T lines and blocks them too).
     const int maxT = (mode == MODE_DIV || !all_phys) ? 1 : tb_max_T();
+    // CSIM_DEBUG_SPLIT=1 (measurement aid): run the single-GPU sweep as the interior + frame pair of
+    // launches on two streams exactly as the multi-GPU loop does, to price the split by itself.
+    static const bool debug_split = tb_env_int("CSIM_DEBUG_SPLIT", 0) != 0;
     int left = nsteps;
     while (left > 0) {
         const int T = left < maxT ? left : maxT;
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_ALL, c->stream, nullptr)) return rc;
+        if (debug_split) {
+            CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+            CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, nullptr)) return rc;
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, nullptr)) return rc;
+            CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));
+            CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        } else {
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_ALL, c->stream, nullptr)) return rc;
+        }
         csim_field_swap(u, tmp);
         left -= T;
     }

@@ -208,6 +208,18 @@ int csim_comm_allreduce_max(csim_ctx* ctx, double* inout, int n);
  * over NVLink, and unpacked by a kernel; all on the context stream. */
 int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
 
+/* Peer-memory halo path (collective over the communicator; call once after csim_comm_init with the
+ * two tiles csim_run_steps will be given).  Every rank maps its up to eight neighbours' tiles and
+ * flag words into its own address space (CUDA IPC between processes, peer access inside one
+ * process).  csim_run_steps then replaces pack → NCCL → unpack by ONE kernel whose CTAs store this
+ * rank's edge bands straight into the neighbours' ghost lines over NVLink and raise a flag there; the
+ * neighbour's frame sweep is gated by a bounded wait on that flag (CSIM_ERR_TIMEOUT, never a hang).
+ * Without this call, or with CSIM_HALO=nccl in the environment, the NCCL path is used.
+ * Call csim_peer_teardown on every rank (after a barrier) before destroying the tiles; destroying a
+ * mapped tile also takes this rank's links down. */
+int csim_peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec);
+int csim_peer_teardown(csim_ctx* ctx);
+
 /* One region of the wide (T-line, 8-neighbour) exchange csim_run_steps performs per T-step block:
  * interior coordinates of its first cell, extent, and the rank on the other side (-1: no such
  * neighbour).  Index k enumerates directions (dx,dy) row by row from (-1,-1) to (1,1) without (0,0). */

@@ -305,7 +305,7 @@ def test_minmax_and_health(csim, ctx):
 
 # ---- multi-GPU halo exchange (needs >= 2 devices; the 1-GPU box skips) ---------------------------
 
-def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors):
+def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors, p2p=False):
     try:
         c = csim.Context(rank)
         c.comm_init(size, rank, uid)
@@ -314,6 +314,8 @@ def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, result
         u = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         tmp = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         u.upload(t0)
+        if p2p:
+            csim.peer_setup(u, tmp, dec)
         p = csim.make_step_params(*phys, csim.BCConfig(*[csim.BCType(b) for b in bc]), dec, 0.0, flags)
         for k in steps:  # several calls: the block structure must not leak across calls
             csim.run_steps(u, tmp, p, dec, k)
@@ -323,12 +325,12 @@ def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, result
         errors.append((rank, repr(e)))
 
 
-def _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=0):
+def _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=0, p2p=False):
     import threading
     uid = csim.comm_unique_id()
     results, errors = {}, []
     th = [threading.Thread(target=_rank_worker, args=(csim, size, r, uid, nxg, nyg, steps, phys, bc, flags,
-                                                      results, errors)) for r in range(size)]
+                                                      results, errors, p2p)) for r in range(size)]
     [t.start() for t in th]
     [t.join(180) for t in th]
     assert not errors, errors
@@ -359,7 +361,9 @@ def test_multi_gpu_matches_single_rank_oracle(csim, oracle_mod, port):
                                       steps=sum(steps), out_every=sum(steps), bc=bc)
             want = port.run(sp)["final"]
             got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc)
-            assert bits_equal(got, want), ("blocked", size, nxg, nyg)
+            assert bits_equal(got, want), ("blocked, NCCL exchange", size, nxg, nyg)
+            got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, p2p=True)
+            assert bits_equal(got, want), ("blocked, peer-memory push", size, nxg, nyg)
             got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=csim.STEP_NO_TEMPORAL)
             assert bits_equal(got, want), ("one-line", size, nxg, nyg)
 
@@ -376,3 +380,21 @@ def test_cpp_dropin_unit_tests():
     assert os.path.exists(exe), "host/build/test_dropin missing: run __graft_entry__.build()"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_multi_process_parity_over_ipc_and_nccl():
+    """One PROCESS per GPU under torchrun (how bench.py runs): the peer-memory path maps the
+    neighbours' tiles with CUDA IPC here, which the threaded test above cannot exercise."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mp_parity_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_PARITY_PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
