@@ -117,6 +117,9 @@ def lib():
             "csim_field_download_interior": [vp, vp],
             "csim_field_upload_async": [vp, vp],
             "csim_field_download_interior_async": [vp, vp],
+            "csim_field_download_interior_be_async": [vp, vp],
+            "csim_event_record": [vp, C.POINTER(vp)],
+            "csim_event_wait": [vp, vp],
             "csim_field_get": [vp, C.c_int, C.c_int, dp],
             "csim_field_set": [vp, C.c_int, C.c_int, C.c_double],
             "csim_field_swap": [vp, vp],
@@ -291,6 +294,11 @@ class Field:
             out = np.empty((self.ny_local, self.nx_local))
         _check(lib().csim_field_download_interior(self._h, _ptr(out)))
         return out
+
+    def download_interior_be_async(self, out: np.ndarray):
+        """De-haloed tile as big-endian doubles (NetCDF wire order) into a pinned buffer, asynchronously."""
+        assert out.size == self.nx_local * self.ny_local and out.flags["C_CONTIGUOUS"]
+        _check(lib().csim_field_download_interior_be_async(self._h, out.ctypes.data_as(C.c_void_p)))
 
     def download_interior_async(self, out: np.ndarray):
         _check(lib().csim_field_download_interior_async(self._h, _ptr(out)))

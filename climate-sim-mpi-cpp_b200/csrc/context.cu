@@ -38,6 +38,20 @@ __global__ void k_fill(double* __restrict__ p, int64_t n, double v) {
         p[k] = v;
 }
 
+// Interior of the pitched tile → dense ny x nx array of big-endian doubles (NetCDF wire order).
+__global__ void __launch_bounds__(256) k_pack_interior_be(const double* __restrict__ in, int nx, int ny,
+                                                          int64_t pitch, unsigned long long* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nx) return;
+    for (int y = blockIdx.y; y < ny; y += gridDim.y) {
+        const unsigned long long v =
+            static_cast<unsigned long long>(__double_as_longlong(in[static_cast<int64_t>(y) * pitch + x]));
+        const unsigned lo = static_cast<unsigned>(v), hi = static_cast<unsigned>(v >> 32);
+        out[static_cast<int64_t>(y) * nx + x] =
+            (static_cast<unsigned long long>(__byte_perm(lo, 0, 0x0123)) << 32) | __byte_perm(hi, 0, 0x0123);
+    }
+}
+
 }  // namespace csim
 
 using namespace csim;
@@ -102,6 +116,7 @@ int csim_ctx_destroy(csim_ctx* c) {
     if (c->ev_go) cudaEventDestroy(c->ev_go);
     if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_wide) cudaFree(c->d_wide);
+    if (c->d_snap) cudaFree(c->d_snap);
     delete c;
     return CSIM_OK;
 }
@@ -233,6 +248,47 @@ int csim_field_download_interior_async(const csim_field* f, double* host) {
                  "csim_field_download_interior_async: null argument");
     return copy2d(f, host, f->nx * sizeof(double), f->interior(), f->pitch * sizeof(double), f->nx, f->ny,
                   cudaMemcpyDeviceToHost, false);
+}
+
+int csim_field_download_interior_be_async(const csim_field* f, void* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID,
+                 "csim_field_download_interior_be_async: null argument");
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    const size_t n = static_cast<size_t>(f->nx) * static_cast<size_t>(f->ny);
+    if (n == 0) return CSIM_OK;
+    if (c->snap_doubles < n) {
+        if (c->d_snap) {
+            CSIM_CUDA(cudaStreamSynchronize(c->stream));
+            CSIM_CUDA(cudaFree(c->d_snap));
+            c->d_snap = nullptr;
+        }
+        CSIM_CUDA(cudaMalloc(&c->d_snap, n * sizeof(double)));
+        c->snap_doubles = n;
+    }
+    const dim3 block(256), grid((f->nx + 255) / 256, f->ny < 1024 ? f->ny : 1024);
+    CSIM_LAUNCH(c, k_pack_interior_be, grid, block, 0, f->interior(), f->nx, f->ny, f->pitch,
+                reinterpret_cast<unsigned long long*>(c->d_snap));
+    CSIM_CUDA(cudaMemcpyAsync(host, c->d_snap, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return CSIM_OK;
+}
+
+int csim_event_record(csim_ctx* c, void** event) {
+    CSIM_REQUIRE(c != nullptr && event != nullptr, CSIM_ERR_INVALID, "csim_event_record: null argument");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e;
+    CSIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+    CSIM_CUDA(cudaEventRecord(e, c->stream));
+    *event = e;
+    return CSIM_OK;
+}
+int csim_event_wait(csim_ctx* c, void* event) {
+    CSIM_REQUIRE(c != nullptr && event != nullptr, CSIM_ERR_INVALID, "csim_event_wait: null argument");
+    CSIM_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e = static_cast<cudaEvent_t>(event);
+    CSIM_CUDA(cudaEventSynchronize(e));
+    CSIM_CUDA(cudaEventDestroy(e));
+    return CSIM_OK;
 }
 
 // check_bounds of src/field.cpp:14-18

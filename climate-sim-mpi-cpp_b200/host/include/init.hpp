@@ -1,0 +1,4 @@
+// init.hpp — forwards to csim_driver.hpp, which declares the reference's include/init.hpp interface
+// for this build (see that file's header for the file:line map).
+#pragma once
+#include "csim_driver.hpp"

@@ -246,9 +246,19 @@ void run_timesteps(Field& u, Field& tmp, const Decomp2D& dec, const BCConfig& bc
     for (int s = 0; s < 4; ++s) p.nbr[s] = c.nbr[s];
     p.bc_value = 0.0;  // src/main.cpp:102
     p.flags = 0;
+    csim_field* du = u.data.device_rw();
+    csim_field* dt_ = tmp.data.device_rw();
+    // more than one rank: map the neighbours' tiles once so halos travel as direct NVLink stores
+    static csim_field* mapped[2] = {nullptr, nullptr};
+    if (csim_host::world().size > 1 && (mapped[0] != du || mapped[1] != dt_)) {
+        const char* h = std::getenv("CSIM_HALO");
+        if (!(h && std::strcmp(h, "nccl") == 0)) check(csim_peer_setup(du, dt_, &c));
+        mapped[0] = du;
+        mapped[1] = dt_;
+    }
     // csim_run_steps swaps the device buffers of the two tiles an odd or even number of times; the
     // newest state ends up in u's handle either way.
-    check(csim_run_steps(u.data.device_rw(), tmp.data.device_rw(), &p, &c, nsteps));
+    check(csim_run_steps(du, dt_, &p, &c, nsteps));
 }
 
 // ---- MPI shim ------------------------------------------------------------------------------------
@@ -329,7 +339,7 @@ int MPI_Barrier(MPI_Comm) {
 }
 int MPI_Reduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, int, MPI_Comm) {
     if (datatype != MPI_DOUBLE || op != MPI_MAX) return 1;
-    std::memcpy(recvbuf, sendbuf, sizeof(double) * static_cast<std::size_t>(count));
+    if (recvbuf != sendbuf) std::memcpy(recvbuf, sendbuf, sizeof(double) * static_cast<std::size_t>(count));
     if (csim_host::world().size > 1)
         check(csim_comm_allreduce_max(csim_host::default_context(), static_cast<double*>(recvbuf), count));
     return MPI_SUCCESS;

@@ -103,6 +103,16 @@ int csim_field_download_interior(const csim_field* f, double* host_dense);
 /* Same, asynchronous on the context stream (host buffer must be pinned; order with csim_sync). */
 int csim_field_upload_async(csim_field* f, const double* host_padded_pinned);
 int csim_field_download_interior_async(const csim_field* f, double* host_dense_pinned);
+/* Snapshot path (src/io.cpp:411-418): the de-haloed tile packed dense AND byte-swapped to big-endian
+ * (the NetCDF wire order) by a kernel, then copied to pinned host memory, asynchronously on the
+ * context stream.  The host bytes can be written to a CDF-5 file as they are. */
+int csim_field_download_interior_be_async(const csim_field* f, void* host_dense_pinned);
+/* Record an event after everything queued on the context stream so far; csim_event_wait blocks the
+ * calling host thread until that point is reached (and releases the event).  Lets a writer thread
+ * wait for one snapshot copy without waiting for the time steps queued behind it. */
+int csim_event_record(csim_ctx* ctx, void** event);
+int csim_event_wait(csim_ctx* ctx, void* event);
+
 /* Field::at(i,j) read / write of one cell in padded coordinates — src/field.cpp:14-29.
  * Out-of-range indices return CSIM_ERR_RANGE (the reference throws std::out_of_range). */
 int csim_field_get(const csim_field* f, int i, int j, double* value);
