@@ -17,53 +17,65 @@
 
 #include "csim_dropin.hpp"
 
+// Initial-condition block of the configuration (include/io.hpp:10-19).
 struct ICConfig {
-    std::string mode = "preset";
-    std::string preset = "gaussian_hotspot";
-    double A = 1.0;
-    double sigma_frac = 0.05;
-    double xc_frac = 0.5;
-    double yc_frac = 0.5;
-    std::string path;
-    std::string var;
+    std::string mode = "preset";              // "preset" | "file" ("file" throws, init.cpp:44-46)
+    std::string preset = "gaussian_hotspot";  // or "constant_zero"
+    double A = 1.0;                           // amplitude
+    double sigma_frac = 0.05;                 // sigma = sigma_frac * min(Lx, Ly)
+    double xc_frac = 0.5;                     // centre, as a fraction of Lx
+    double yc_frac = 0.5;                     // centre, as a fraction of Ly
+    std::string path;                         // parsed, unused upstream
+    std::string var;                          // parsed from YAML only; the CLI value is dropped upstream
 };
 
+// Everything the run needs (include/io.hpp:21-39); defaults are the reference's.
 struct SimConfig {
-    int nx = 256, ny = 256;
-    double dx = 1.0, dy = 1.0;
-
-    double D = 0.0;
-    double vx = 0.0, vy = 0.0;
-
-    double dt = 0.1;
+    int nx = 256;  // global grid
+    int ny = 256;
+    double dx = 1.0;  // spacing
+    double dy = 1.0;
+    double D = 0.0;  // diffusivity
+    double vx = 0.0;  // constant velocity
+    double vy = 0.0;
+    double dt = 0.1;  // clamped to safe_dt by the driver
     int steps = 100;
-    int out_every = 50;
-
-    BCConfig bc;
-
-    std::string output_prefix = "snap";
-
+    int out_every = 50;  // a frame at the start of every out_every-th step
+    BCConfig bc;         // four sides, Dirichlet by default
+    std::string output_prefix = "snap";  // parsed; the output path is fixed (main.cpp:87)
     ICConfig ic{};
 
-    void validate() const;  // throws std::runtime_error with the reference's messages (io.cpp:58-69)
+    // throws std::runtime_error with the reference's messages (io.cpp:58-69)
+    void validate() const;
 };
 
+// Values given on the command line (include/io.hpp:41-62); an empty optional keeps the YAML/default.
 struct CLIOverrides {
-    std::optional<int> nx, ny;
-    std::optional<double> dx, dy;
-
-    std::optional<double> D, vx, vy;
-
+    std::optional<int> nx;
+    std::optional<int> ny;
+    std::optional<double> dx;
+    std::optional<double> dy;
+    std::optional<double> D;
+    std::optional<double> vx;
+    std::optional<double> vy;
     std::optional<double> dt;
-    std::optional<int> steps, out_every;
-
-    std::optional<BCType> bc_left, bc_right, bc_bottom, bc_top;
-
+    std::optional<int> steps;
+    std::optional<int> out_every;
+    std::optional<BCType> bc_left;
+    std::optional<BCType> bc_right;
+    std::optional<BCType> bc_bottom;
+    std::optional<BCType> bc_top;
     std::optional<std::string> output_prefix;
-
-    struct {
-        std::optional<std::string> mode, preset, path, format, var;
-        std::optional<double> A, sigma_frac, xc_frac, yc_frac;
+    struct IC {
+        std::optional<std::string> mode;
+        std::optional<std::string> preset;
+        std::optional<std::string> path;
+        std::optional<std::string> format;  // never parsed upstream either
+        std::optional<std::string> var;
+        std::optional<double> A;
+        std::optional<double> sigma_frac;
+        std::optional<double> xc_frac;
+        std::optional<double> yc_frac;
     } ic;
 };
 

@@ -398,3 +398,22 @@ def test_multi_process_parity_over_ipc_and_nccl():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mp_parity_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MP_PARITY_PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("env", [{"CSIM_TB_MAXT": "4"}, {"CSIM_TB_MAXT": "2"}, {"CSIM_TB_MAXT": "1"},
+                                 {"CSIM_TB_MAXT": "3", "CSIM_TB_CHUNK": "7", "CSIM_TB_EDGE_SPLIT": "3"},
+                                 {"CSIM_TB_MAXT": "4", "CSIM_TB_CHUNK": "500", "CSIM_TB_EDGE_SPLIT": "1",
+                                  "CSIM_TB_PF": "0"}])
+def test_every_blocking_depth_and_chunking_matches_golden(env):
+    """The sweep is instantiated for T = 1..4; the default run uses T <= 3.  Each depth, odd chunk
+    heights and edge splits must give the same bits (the knobs are read once per process → subprocess)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden_runner.py")], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"T={env['CSIM_TB_MAXT']} " in r.stdout
