@@ -67,9 +67,12 @@ struct TbArgs {
 
 template <int MODE, bool VXP, bool VYP>
 __device__ __forceinline__ double tb_update(double c, double w, double e, double s, double n, const StepK& k) {
-    const double c2 = __dmul_rn(2.0, c);
-    double lx = __dadd_rn(__dsub_rn(e, c2), w);
-    double ly = __dadd_rn(__dsub_rn(n, c2), s);
+    // e - 2.0*c and n - 2.0*c as one FMA each: 2.0*c is exact (a power-of-two scaling), so
+    // fma(-2, c, e) rounds the same real number as the reference's (e - 2.0*c) — one rounding either
+    // way — as long as 2|c| does not overflow (|c| < 2^1023; csim_field_health reports max|u|).
+    // Every other product of the update is rounded separately in the reference and stays unfused.
+    double lx = __dadd_rn(__fma_rn(-2.0, c, e), w);
+    double ly = __dadd_rn(__fma_rn(-2.0, c, n), s);
     if (MODE == MODE_RECIP) {
         lx = __dmul_rn(lx, k.rdx2);
         ly = __dmul_rn(ly, k.rdy2);
@@ -245,8 +248,16 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
             src += 2 * a.pitch;
         }
     }
-    tb_store_row(a, ln, lane, lane_store_all, r - T, ya, yb, fin[0]);
-    tb_store_row(a, ln, lane, lane_store_all, r - T + 1, ya, yb, fin[1]);
+    if (!GEN) {
+        // fast ticks run only in strips where every lane stores all four cells or none, and the rows
+        // they finish are interior rows: one predicated 256-bit store per row, no per-cell tests
+        double* dst = a.out + static_cast<long long>(r - T) * a.pitch + ln.x0;
+        if (lane_store_all && r - T >= ya && r - T < yb) tb_store4(dst, fin[0]);
+        if (lane_store_all && r - T + 1 >= ya && r - T + 1 < yb) tb_store4(dst + a.pitch, fin[1]);
+    } else {
+        tb_store_row(a, ln, lane, lane_store_all, r - T, ya, yb, fin[0]);
+        tb_store_row(a, ln, lane, lane_store_all, r - T + 1, ya, yb, fin[1]);
+    }
 }
 
 template <int T, int MODE, bool VXP, bool VYP>
@@ -282,8 +293,12 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     TbLane ln;
     ln.x0 = xb + lane * kTbCells;
     const bool can_load = ln.x0 + 3 < a.xmax_load;
-    const bool strip_fast = xb >= a.fx0 && xb + kTbWidth <= a.fx1;
     const bool lane_store_all = lane >= 1 && lane <= 30 && ln.x0 >= a.sx0 && ln.x0 + 3 < a.sx1;
+    // a lane that stores some but not all of its cells (the store range ends inside its group) needs
+    // the per-cell store of the general path; fast strips have none
+    const bool lane_partial = !lane_store_all && lane >= 1 && lane <= 30 && ln.x0 + 3 >= a.sx0 && ln.x0 < a.sx1;
+    const bool strip_fast =
+        xb >= a.fx0 && xb + kTbWidth <= a.fx1 && __ballot_sync(0xffffffffu, lane_partial) == 0u;
     {
         const bool physL = a.phys & 1, physR = a.phys & 2;
         ln.inx = 0;
