@@ -132,6 +132,7 @@ def lib():
             "csim_step_fused": [vp, vp, C.POINTER(StepParams), C.c_int],
             "csim_minmax": [vp, dp, dp],
             "csim_field_health": [vp, dp, C.POINTER(C.c_uint64)],
+            "csim_field_value_state": [vp],
             "csim_decomp_init": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Decomp)],
             "csim_comm_unique_id": [C.c_char_p],
             "csim_comm_init": [vp, C.c_int, C.c_int, C.c_char_p],
@@ -318,6 +319,11 @@ class Field:
         m, n = C.c_double(), C.c_uint64()
         _check(lib().csim_field_health(self._h, C.byref(m), C.byref(n)))
         return m.value, int(n.value)
+
+    @property
+    def value_state(self):
+        """0 unknown, 1 clean, 2 tainted (csim_field_value_state)."""
+        return int(lib().csim_field_value_state(self._h))
 
     def close(self):
         if self._h:

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <algorithm>
+
 #include "csim_internal.hpp"
 
 namespace csim {
@@ -101,6 +103,15 @@ int csim_ctx_destroy(csim_ctx* c) {
     cudaSetDevice(c->device);
     csim_peer_teardown(c);
     if (c->comm) csim_comm_destroy(c);
+    // tiles that outlive their context (garbage-collection order in a host language) are orphaned:
+    // their device memory goes now, csim_field_destroy later only frees the handle
+    cudaDeviceSynchronize();
+    for (csim_field* f : c->fields) {
+        if (f->base) cudaFree(f->base);
+        f->base = nullptr;
+        f->ctx = nullptr;
+    }
+    c->fields.clear();
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
@@ -166,12 +177,19 @@ int csim_field_create(csim_ctx* c, int nx, int ny, int halo, double dx, double d
         delete f;
         return cuda_fail(e, "cudaMemsetAsync(field)", __FILE__, __LINE__);
     }
+    c->fields.push_back(f);
     *out = f;
     return CSIM_OK;
 }
 
 int csim_field_destroy(csim_field* f) {
     if (!f) return CSIM_OK;
+    if (!f->ctx) {  // the context went first and already released the device memory
+        delete f;
+        return CSIM_OK;
+    }
+    auto& reg = f->ctx->fields;
+    reg.erase(std::remove(reg.begin(), reg.end(), f), reg.end());
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->stream_x);
@@ -208,6 +226,7 @@ int csim_field_fill(csim_field* f, double value) {
     // superset and keeps the wide-halo padding defined.
     const int64_t n = f->pitch * f->rows;
     CSIM_LAUNCH(c, k_fill, c->sm_count * 8, 256, 0, f->base, n, value);
+    f->values = csim_field::kUnknown;
     return CSIM_OK;
 }
 
@@ -224,11 +243,13 @@ static int copy2d(const csim_field* f, void* dst, size_t dpitch, const void* src
 
 int csim_field_upload(csim_field* f, const double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload: null argument");
+    f->values = csim_field::kUnknown;
     return copy2d(f, f->at(0, 0), f->pitch * sizeof(double), host, f->nxt() * sizeof(double), f->nxt(),
                   f->nyt(), cudaMemcpyHostToDevice, true);
 }
 int csim_field_upload_async(csim_field* f, const double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload_async: null argument");
+    f->values = csim_field::kUnknown;
     return copy2d(f, f->at(0, 0), f->pitch * sizeof(double), host, f->nxt() * sizeof(double), f->nxt(),
                   f->nyt(), cudaMemcpyHostToDevice, false);
 }
@@ -309,6 +330,7 @@ int csim_field_set(csim_field* f, int i, int j, double value) {
     CSIM_CUDA(cudaSetDevice(f->ctx->device));
     CSIM_CUDA(cudaMemcpyAsync(f->at(i, j), &value, sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
     CSIM_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    f->values = csim_field::kUnknown;
     return CSIM_OK;
 }
 
@@ -323,6 +345,9 @@ int csim_field_swap(csim_field* a, csim_field* b) {
     double* t = a->base;
     a->base = b->base;
     b->base = t;
+    const int v = a->values;
+    a->values = b->values;
+    b->values = v;
     return CSIM_OK;
 }
 
@@ -333,6 +358,7 @@ int csim_field_copy(const csim_field* src, csim_field* dst) {
     CSIM_CUDA(cudaMemcpyAsync(dst->base, src->base,
                               static_cast<size_t>(src->pitch) * src->rows * sizeof(double),
                               cudaMemcpyDeviceToDevice, src->ctx->stream));
+    dst->values = src->values;
     return CSIM_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "csim.h"
 
@@ -18,8 +19,11 @@ constexpr int kTailX = 16;
 constexpr int kLeadY = 8;
 constexpr int kMaxHalo = 8;
 
+struct csim_field;
+
 struct csim_ctx {
     int device = 0;
+    std::vector<csim_field*> fields;  // live tiles of this context (orphaned by csim_ctx_destroy)
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     // scratch for reductions: device partials + pinned host landing zone
@@ -62,6 +66,12 @@ struct csim_field {
     double dx = 1.0, dy = 1.0;
     int64_t pitch = 0, rows = 0;
     double* base = nullptr;
+    // What the library knows about the VALUES of the padded tile (kernels.cu, resolve_zero_terms):
+    // kUnknown after any write from outside the step kernels, kClean once a scan found every cell
+    // finite, below 2^1000 in magnitude and not -0.0, kTainted once a scan found otherwise.  The fused
+    // step preserves kClean under a monotone time step, so a run scans once per upload.
+    enum { kUnknown = 0, kClean = 1, kTainted = 2 };
+    int values = kUnknown;
     double* interior() const { return base + static_cast<int64_t>(kLeadY) * pitch + kLeadX; }
     int nxt() const { return nx + 2 * h; }
     int nyt() const { return ny + 2 * h; }
@@ -84,8 +94,13 @@ int tb_max_T();
 bool tb_split_pointless(int nchunks, int n_int);
 // kernels.cu
 int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mode);
+// May the sweep drop the advection term of a velocity component that is exactly +0.0 (tb_update)?
+// Scans `u` if its state is unknown; with `collective` every rank of the communicator must call it
+// (one MAX reduction makes the answer the same everywhere).
+int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k, int mode, int maxT,
+                       bool collective, bool* allowed);
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T, int part, cudaStream_t stream, bool* launched);
+                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms = false);
 
 }  // namespace csim
 

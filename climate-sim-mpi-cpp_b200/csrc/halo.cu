@@ -507,6 +507,7 @@ int csim_halo_exchange(csim_field* f, const csim_decomp* dec) {
     CSIM_REQUIRE(f->h == 1, CSIM_ERR_UNSUPPORTED, "csim_halo_exchange: needs halo == 1 (main.cpp:65)");
     csim_ctx* c = f->ctx;
     CSIM_REQUIRE(c->comm != nullptr, CSIM_ERR_COMM, "csim_halo_exchange: tile has neighbours but no communicator");
+    f->values = csim_field::kUnknown;  // ghost lines now hold a neighbour's cells
     for (int s = 0; s < 4; ++s)
         CSIM_REQUIRE(dec->nbr[s] == CSIM_PROC_NULL || (dec->nbr[s] >= 0 && dec->nbr[s] < c->comm_size),
                      CSIM_ERR_INVALID, "csim_halo_exchange: neighbour rank outside the communicator");
@@ -601,6 +602,12 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     //               before the frame's event arrives and the frame waits a whole round for slots:
     //               measured chain frame-wait 88 + frame 88 + exchange 132 us = 308 us per block
     //               against 285 us of work (profiles/r01_multigpu_phases.md).
+    // one decision for the whole call, the same on every rank (csim_run_steps is collective)
+    bool zero_terms = false;
+    if (nsteps >= maxT)
+        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, true, &zero_terms)) return rc;
+    const int values_after = zero_terms ? csim_field::kClean
+                                        : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
     const bool p2p = peer_path_enabled(c, u, tmp);
     if (p2p && *c->h_err)
         return fail(CSIM_ERR_TIMEOUT, "csim_run_steps: a neighbour's halo did not arrive within the bounded wait");
@@ -617,11 +624,12 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
         bool launched = false;
         if (!first) CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));  // interior(n-1) done
         CSIM_CUDA(cudaEventRecord(c->ev_go, c->stream_x));                       // go(n)
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched)) return rc;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched, zero_terms)) return rc;
         CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));                     // frame(n) done
         CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_go, 0));
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched)) return rc;
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched, zero_terms)) return rc;
         CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));                       // interior(n) done
+        tmp->values = values_after;
         csim_field_swap(u, tmp);
         left -= T;
         first = false;

@@ -257,6 +257,23 @@ __global__ void __launch_bounds__(256) k_health(const double* __restrict__ f, in
     }
 }
 
+// Value scan behind resolve_zero_terms: counts the cells of the padded tile that are not finite, are
+// 2^1000 or larger in magnitude, or are -0.0.  f addresses padded cell (0,0).
+__global__ void __launch_bounds__(256) k_scan_values(const double* __restrict__ f, int nxt, int nyt, int64_t pitch,
+                                                     unsigned long long* __restrict__ bad_out) {
+    unsigned long long bad = 0;
+    for (int j = blockIdx.x; j < nyt; j += gridDim.x) {
+        const double* row = f + static_cast<int64_t>(j) * pitch;
+        for (int i = threadIdx.x; i < nxt; i += blockDim.x) {
+            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(row[i]));
+            // exponent field >= 1000 + 1023 covers inf and NaN as well
+            if (((b >> 52) & 0x7ffull) >= 2023ull || b == 0x8000000000000000ull) ++bad;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(bad_out, bad);
+}
+
 StepK make_consts(double dx, double dy, double D, double vx, double vy, double dt, int flags, bool* use_div) {
     StepK k;
     k.dtD = dt * D;  // "dt * D * lap" groups as (dt*D)*lap, src/diffusion.cpp:14
@@ -337,8 +354,76 @@ static int tb_env_int(const char* name, int dflt) {
 // part: TB_ALL, or TB_INTERIOR / TB_FRAME to split the sweep into the work items that do not / do
 // read ghost lines, so the former can run while the exchange is in flight.  Returns CSIM_OK and
 // sets *launched = false when the requested part is empty.
+static bool is_pos_zero(double v) {
+    uint64_t b;
+    std::memcpy(&b, &v, sizeof b);
+    return b == 0;
+}
+bool tb_has_zero_variant(int T, int mode) { return (T == 3 || T == 4) && (mode == MODE_UNIT || mode == MODE_RECIP); }
+
+// See csim_internal.hpp.  The dropped-term kernels are bit-identical to the full ones when (tb_update)
+//   (1) every cell the sweep reads is finite and no cell is -0.0              → scanned here, once
+//       per upload; kept by the step kernels: an update only yields -0 from c == -0, and
+//   (2) the field stays finite                                                → the step is a convex
+//       combination of the five cells when dt*(2D(1/dx²+1/dy²) + |vx|/dx + |vy|/dy) <= 1 (max
+//       principle; the scan bounds |u| by 2^1000, so rounding cannot carry it to overflow), and
+//   (3) every rank decides alike (halo cells are advanced redundantly on both sides of an edge).
+// Anything else — a tainted tile, a non-monotone step, a -0.0 or negative-zero velocity — runs the
+// full arithmetic.
+int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k, int mode, int maxT,
+                       bool collective, bool* allowed) {
+    *allowed = false;
+    static const bool off = tb_env_int("CSIM_ZERO_TERMS", 1) == 0;
+    const bool candidate = !off && tb_has_zero_variant(maxT, mode) && (is_pos_zero(k.vx) || is_pos_zero(k.vy));
+    if (!candidate) return CSIM_OK;  // decided from the parameters alone: identical on every rank
+    bool ok = std::isfinite(p->bc_value) && std::fabs(p->bc_value) < 0x1p1000 && p->dt > 0.0 && p->D >= 0.0;
+    if (ok) {
+        const double w = p->dt * (2.0 * p->D * (1.0 / (u->dx * u->dx) + 1.0 / (u->dy * u->dy)) +
+                                  std::fabs(p->vx) / u->dx + std::fabs(p->vy) / u->dy);
+        ok = w <= 1.0;  // NaN compares false
+    }
+    csim_ctx* c = u->ctx;
+    if (ok && u->values == csim_field::kUnknown) {
+        auto* d_bad = reinterpret_cast<unsigned long long*>(c->d_scratch);
+        CSIM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+        if (u->nxt() > 0 && u->nyt() > 0) {
+            int nblocks = c->sm_count * 8;
+            if (nblocks > u->nyt()) nblocks = u->nyt();
+            CSIM_LAUNCH(c, k_scan_values, nblocks, 256, 0, u->at(0, 0), u->nxt(), u->nyt(), u->pitch, d_bad);
+        }
+        CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  c->stream));
+        CSIM_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned long long bad = 0;
+        std::memcpy(&bad, c->h_scratch, sizeof bad);
+        u->values = bad ? csim_field::kTainted : csim_field::kClean;
+    }
+    ok = ok && u->values == csim_field::kClean;
+    if (collective) {
+        double veto = ok ? 0.0 : 1.0;
+        if (int rc = csim_comm_allreduce_max(c, &veto, 1)) return rc;
+        ok = veto == 0.0;
+    }
+    *allowed = ok;
+    return CSIM_OK;
+}
+
+cudaError_t tb_launch(int vxs, int vys, int kind, int T, int mode, const TbArgs& a, cudaStream_t stream) {
+    switch ((vxs + 1) * 3 + (vys + 1)) {
+        case 0: return tb_launch_nn(kind, T, mode, a, stream);
+        case 1: return tb_launch_nz(kind, T, mode, a, stream);
+        case 2: return tb_launch_np(kind, T, mode, a, stream);
+        case 3: return tb_launch_zn(kind, T, mode, a, stream);
+        case 4: return tb_launch_zz(kind, T, mode, a, stream);
+        case 5: return tb_launch_zp(kind, T, mode, a, stream);
+        case 6: return tb_launch_pn(kind, T, mode, a, stream);
+        case 7: return tb_launch_pz(kind, T, mode, a, stream);
+        default: return tb_launch_pp(kind, T, mode, a, stream);
+    }
+}
+
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T, int part, cudaStream_t stream, bool* launched) {
+                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms) {
     csim_ctx* c = u->ctx;
     const int nx = u->nx, ny = u->ny;
     TbArgs a;
@@ -371,9 +456,16 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.value = p->bc_value;
     a.k = k;
     a.xmax_load = static_cast<int>(u->pitch) - kLeadX;
+    // kind 1 = k_step_tb (two rows per tick), the default; CSIM_TB_KERNEL=ring selects k_step_ring
+    // (one row per tick, rotating ring of row slots), which is parity-tested and kept for A/B timing
+    static const int kind = [] {
+        const char* e = std::getenv("CSIM_TB_KERNEL");
+        return (e && std::strcmp(e, "ring") == 0) ? 0 : 1;
+    }();
     a.pf_rows = tb_env_int("CSIM_TB_PF", 4);
     a.row_limit = a.pf_rows > 0 ? ny + kLeadY : -(1 << 30);  // <= 0 disables the prefetch branch
     if (a.pf_rows < 0) a.pf_rows = 0;
+    a.pf_off = static_cast<long long>(a.pf_rows) * u->pitch;
     a.nstrips = (nx + kTbWout - 1) / kTbWout;
     if (a.nstrips < 1) a.nstrips = 1;
     a.edge_split = tb_env_int("CSIM_TB_EDGE_SPLIT", 2);
@@ -381,7 +473,7 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     // chunk height: fill k whole rounds of the resident warp slots of the machine
     const int rows = a.sy1 - a.sy0;
     const int n_edge = a.nstrips >= 2 ? 2 : 1, n_int = a.nstrips - n_edge;
-    const int slots = c->sm_count * kTbBlocksPerSM * kTbWarpsPerBlock;
+    const int slots = c->sm_count * (kind == 0 ? kRingBlocksPerSM : kTbBlocksPerSM) * kTbWarpsPerBlock;
     const int weight = n_int + n_edge * a.edge_split;
     // Chunk height.  A launch runs as several rounds of resident warps; short chunks keep the last
     // round from idling the machine, tall chunks amortise the 2T rows each chunk re-computes.
@@ -390,6 +482,27 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     if (ch <= 0) {
         const long long want = static_cast<long long>(rows) * weight / (2LL * slots);  // >= 2 rounds
         ch = static_cast<int>(want < 32 ? 32 : (want > 96 ? 96 : want));
+        if (kind == 0) {
+            // k_step_ring runs its hot code in groups of N = 2T+3 ticks and a chunk of h rows takes
+            // h + 2T ticks: pick h so that the groups tile the chunk exactly, and among those heights
+            // the one with the least (rounds of resident warps) x (ticks per chunk)
+            const int N = CSIM_RING_U < ring_slots(T) ? CSIM_RING_U : ring_slots(T);
+            long long best_cost = -1;
+            for (int m = 4; m <= 64; ++m) {
+                const int hc = m * N - 2 * T;
+                if (hc < 32 || hc > 160) continue;
+                const long long nch = (rows + hc - 1) / hc;
+                const long long items = nch * n_int + ((rows + (hc + a.edge_split - 1) / a.edge_split - 1) /
+                                                       ((hc + a.edge_split - 1) / a.edge_split)) * n_edge;
+                const long long rounds = (items + slots - 1) / slots;
+                // a partly filled last round still costs a whole chunk time
+                const long long cost = rounds * (hc + 2 * T);
+                if (best_cost < 0 || cost < best_cost) {
+                    best_cost = cost;
+                    ch = hc;
+                }
+            }
+        }
     }
     if (ch > rows) ch = rows;
     if (ch < 1) ch = 1;
@@ -417,16 +530,15 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.n_items = n_int * int_chunks + a.n_edge_items;
     if (a.n_items <= 0) return CSIM_OK;
     if (launched) *launched = true;
-    cudaError_t e;
-    const bool vxp = k.vx_pos != 0, vyp = k.vy_pos != 0;
-    if (vxp && vyp)
-        e = tb_launch_pp(T, mode, a, stream);
-    else if (vxp)
-        e = tb_launch_pn(T, mode, a, stream);
-    else if (vyp)
-        e = tb_launch_np(T, mode, a, stream);
-    else
-        e = tb_launch_nn(T, mode, a, stream);
+    // upwind selectors; a component that is exactly +0.0 may drop its term (tb_update) when the
+    // caller established the conditions (zero_terms) and the variant is instantiated
+    int vxs = k.vx_pos ? 1 : -1, vys = k.vy_pos ? 1 : -1;
+    static const bool force_zero = tb_env_int("CSIM_ZERO_TERMS_FORCE", 0) != 0;  // measurement aid only
+    if ((zero_terms || force_zero) && tb_has_zero_variant(T, mode)) {
+        if (is_pos_zero(k.vx)) vxs = 0;
+        if (is_pos_zero(k.vy)) vys = 0;
+    }
+    const cudaError_t e = tb_launch(vxs, vys, kind, T, mode, a, stream);
     ++c->launches;
     if (e != cudaSuccess) return cuda_fail(e, "k_step_tb", __FILE__, __LINE__);
     return CSIM_OK;
@@ -462,6 +574,7 @@ extern "C" {
 
 int csim_diffusion_step(const csim_field* u, csim_field* out, double D, double dt) {
     if (int rc = check_pair(u, out, "csim_diffusion_step")) return rc;
+    out->values = csim_field::kUnknown;
     csim_ctx* c = u->ctx;
     CSIM_CUDA(cudaSetDevice(c->device));
     bool use_div = false;
@@ -485,6 +598,7 @@ int csim_diffusion_step(const csim_field* u, csim_field* out, double D, double d
 
 int csim_advection_step(const csim_field* u, csim_field* out, double vx, double vy, double dt) {
     if (int rc = check_pair(u, out, "csim_advection_step")) return rc;
+    out->values = csim_field::kUnknown;
     csim_ctx* c = u->ctx;
     CSIM_CUDA(cudaSetDevice(c->device));
     bool use_div = false;
@@ -506,6 +620,7 @@ int csim_apply_boundary(csim_field* f, const int nbr[4], const int bc[4], double
     CSIM_REQUIRE(f != nullptr && nbr != nullptr && bc != nullptr, CSIM_ERR_INVALID,
                  "csim_apply_boundary: null argument");
     CSIM_CUDA(cudaSetDevice(f->ctx->device));
+    f->values = csim_field::kUnknown;
     return launch_boundary(f, nbr, bc, value);
 }
 
@@ -528,6 +643,7 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
         for (int n = 0; n < nsteps; ++n) {
             if (int rc = launch_boundary(u, p->nbr, p->bc, p->bc_value)) return rc;  // main.cpp:102
             if (int rc = launch_step_v1(u, tmp, k, mode == MODE_DIV)) return rc;     // main.cpp:104-107
+            u->values = tmp->values = csim_field::kUnknown;
             csim_field_swap(u, tmp);                                                 // main.cpp:109
         }
         return CSIM_OK;
@@ -541,19 +657,25 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     // CSIM_DEBUG_SPLIT=1 (measurement aid): run the single-GPU sweep as the interior + frame pair of
     // launches on two streams exactly as the multi-GPU loop does, to price the split by itself.
     static const bool debug_split = tb_env_int("CSIM_DEBUG_SPLIT", 0) != 0;
+    bool zero_terms = false;
+    if (nsteps >= maxT)
+        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, false, &zero_terms)) return rc;
+    const int values_after = zero_terms ? csim_field::kClean
+                                        : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
     int left = nsteps;
     while (left > 0) {
         const int T = left < maxT ? left : maxT;
         if (debug_split) {
             CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
             CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
-            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, nullptr)) return rc;
-            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, nullptr)) return rc;
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, nullptr, zero_terms)) return rc;
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, nullptr, zero_terms)) return rc;
             CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));
             CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         } else {
-            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_ALL, c->stream, nullptr)) return rc;
+            if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_ALL, c->stream, nullptr, zero_terms)) return rc;
         }
+        tmp->values = values_after;  // tmp is rewritten from u; a clean u under a monotone step stays clean
         csim_field_swap(u, tmp);
         left -= T;
     }
@@ -578,6 +700,8 @@ int csim_minmax(const csim_field* f, double* mn, double* mx) {
     *mx = c->h_scratch[1];
     return CSIM_OK;
 }
+
+int csim_field_value_state(const csim_field* f) { return f ? f->values : -1; }
 
 int csim_field_health(const csim_field* f, double* max_abs, uint64_t* nonfinite) {
     CSIM_REQUIRE(f != nullptr && max_abs != nullptr && nonfinite != nullptr, CSIM_ERR_INVALID,

@@ -58,6 +58,7 @@ struct TbArgs {
     int frame_pair;    // ... or, if set, exactly the first and the last chunk of every interior strip
     int xmax_load;     // a lane may load its 4 cells iff x0+3 < xmax_load (row allocation bound)
     int pf_rows;       // L2 prefetch distance in rows (0 = off)
+    long long pf_off;  // pf_rows * pitch
     int row_limit;     // rows y < row_limit are inside the allocation
     int phys;          // bit s: side s (left,right,bottom,top) is a physical boundary
     int bcL, bcR, bcB, bcT;
@@ -65,7 +66,14 @@ struct TbArgs {
     StepK k;
 };
 
-template <int MODE, bool VXP, bool VYP>
+// One cell update.  VXS / VYS select the upwind side: +1 for v >= 0 (backward difference), -1 for
+// v < 0 (forward difference), 0 for a velocity component that is exactly +0.0, whose whole term is
+// dropped.  Dropping is exact for finite fields without negative zeros: (+0)*d is a signed zero, q + (±0)
+// equals q unless q is itself a zero, and the sign of a zero `adv` can only change the result when
+// o == -0, which needs c == -0 (x + y is -0 only for (-0) + (-0)); by the same argument an update never
+// creates a -0 where there was none.  The dispatcher (kernels.cu, zero_terms_allowed) uses the 0
+// variants only for fields it has scanned (finite, no -0, on every rank) and a stable time step.
+template <int MODE, int VXS, int VYS>
 __device__ __forceinline__ double tb_update(double c, double w, double e, double s, double n, const StepK& k) {
     // e - 2.0*c and n - 2.0*c as one FMA each: 2.0*c is exact (a power-of-two scaling), so
     // fma(-2, c, e) rounds the same real number as the reference's (e - 2.0*c) — one rounding either
@@ -81,16 +89,21 @@ __device__ __forceinline__ double tb_update(double c, double w, double e, double
         ly = __ddiv_rn(ly, k.dy2);
     }
     const double o = __dadd_rn(c, __dmul_rn(k.dtD, __dadd_rn(lx, ly)));
-    double ddx = VXP ? __dsub_rn(c, w) : __dsub_rn(e, c);
-    double ddy = VYP ? __dsub_rn(c, s) : __dsub_rn(n, c);
-    if (MODE == MODE_RECIP) {
-        ddx = __dmul_rn(ddx, k.rdx);
-        ddy = __dmul_rn(ddy, k.rdy);
-    } else if (MODE == MODE_DIV) {
-        ddx = __ddiv_rn(ddx, k.dx);
-        ddy = __ddiv_rn(ddy, k.dy);
+    if (VXS == 0 && VYS == 0) return o;
+    double px = 0.0, py = 0.0;
+    if (VXS != 0) {
+        double ddx = VXS > 0 ? __dsub_rn(c, w) : __dsub_rn(e, c);
+        if (MODE == MODE_RECIP) ddx = __dmul_rn(ddx, k.rdx);
+        if (MODE == MODE_DIV) ddx = __ddiv_rn(ddx, k.dx);
+        px = __dmul_rn(k.vx, ddx);
     }
-    const double adv = __dadd_rn(__dmul_rn(k.vx, ddx), __dmul_rn(k.vy, ddy));
+    if (VYS != 0) {
+        double ddy = VYS > 0 ? __dsub_rn(c, s) : __dsub_rn(n, c);
+        if (MODE == MODE_RECIP) ddy = __dmul_rn(ddy, k.rdy);
+        if (MODE == MODE_DIV) ddy = __ddiv_rn(ddy, k.dy);
+        py = __dmul_rn(k.vy, ddy);
+    }
+    const double adv = VXS == 0 ? py : (VYS == 0 ? px : __dadd_rn(px, py));
     return __dadd_rn(o, __dmul_rn(k.ndt, adv));
 }
 
@@ -114,16 +127,16 @@ struct TbLane {
 // rows).  GEN = true: every boundary rule of the reference (see the file header); all conditions on
 // j are warp-uniform, all conditions on x are per-lane selects, so the four stencils still
 // interleave.
-template <int MODE, bool VXP, bool VYP, bool GEN>
+template <int MODE, int VXS, int VYS, bool GEN>
 __device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j, const double (&s)[4],
                                        const double (&c)[4], const double (&n)[4], double (&res)[4]) {
     const double w0 = __shfl_up_sync(0xffffffffu, c[3], 1);
     const double e3 = __shfl_down_sync(0xffffffffu, c[0], 1);
     if (!GEN) {
-        res[0] = tb_update<MODE, VXP, VYP>(c[0], w0, c[1], s[0], n[0], a.k);
-        res[1] = tb_update<MODE, VXP, VYP>(c[1], c[0], c[2], s[1], n[1], a.k);
-        res[2] = tb_update<MODE, VXP, VYP>(c[2], c[1], c[3], s[2], n[2], a.k);
-        res[3] = tb_update<MODE, VXP, VYP>(c[3], c[2], e3, s[3], n[3], a.k);
+        res[0] = tb_update<MODE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k);
+        res[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k);
+        res[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k);
+        res[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k);
         return;
     }
     const bool physB = a.phys & 4, physT = a.phys & 8;
@@ -168,10 +181,10 @@ __device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j,
         if (i == ln.ghost_r) keep[i] = bc_pick(a.bcR, a.value, i == 0 ? w0 : c[i == 0 ? 0 : i - 1], c[i]);  // x == nx
     }
     double r[4];
-    r[0] = tb_update<MODE, VXP, VYP>(c[0], ww0, ee[0], ss[0], nn[0], a.k);
-    r[1] = tb_update<MODE, VXP, VYP>(c[1], c[0], ee[1], ss[1], nn[1], a.k);
-    r[2] = tb_update<MODE, VXP, VYP>(c[2], c[1], ee[2], ss[2], nn[2], a.k);
-    r[3] = tb_update<MODE, VXP, VYP>(c[3], c[2], ee[3], ss[3], nn[3], a.k);
+    r[0] = tb_update<MODE, VXS, VYS>(c[0], ww0, ee[0], ss[0], nn[0], a.k);
+    r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], ee[1], ss[1], nn[1], a.k);
+    r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], ee[2], ss[2], nn[2], a.k);
+    r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], ee[3], ss[3], nn[3], a.k);
 #pragma unroll
     for (int i = 0; i < 4; ++i) res[i] = ((ln.inx >> i) & 1) ? r[i] : keep[i];
 }
@@ -218,7 +231,7 @@ __device__ __forceinline__ void tb_store_row(const TbArgs& a, const TbLane& ln, 
 // state (rows r-k-2, r-k-1) and slot 1-PH its incoming pair (rows r-k, r-k+1); afterwards the
 // incoming pair is the state and slot PH is free for the next pair, so consecutive ticks alternate PH
 // and no register is ever moved.
-template <int T, int MODE, bool VXP, bool VYP, int PH, bool GEN>
+template <int T, int MODE, int VXS, int VYS, int PH, bool GEN>
 __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int lane, bool lane_store_all,
                                         bool can_load, int r, int ya, int yb, const double*& src,
                                         double (&st)[T][2][2][4]) {
@@ -230,11 +243,11 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
         double(&C)[4] = st[k][1 - PH][0];
         double(&D)[4] = st[k][1 - PH][1];
         if (k + 1 < T) {
-            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k - 1, A, B, C, st[k + 1 < T ? k + 1 : k][1 - PH][0]);
-            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k, B, C, D, st[k + 1 < T ? k + 1 : k][1 - PH][1]);
+            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k - 1, A, B, C, st[k + 1 < T ? k + 1 : k][1 - PH][0]);
+            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k, B, C, D, st[k + 1 < T ? k + 1 : k][1 - PH][1]);
         } else {
-            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k - 1, A, B, C, fin[0]);
-            tb_row<MODE, VXP, VYP, GEN>(a, ln, r - k, B, C, D, fin[1]);
+            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k - 1, A, B, C, fin[0]);
+            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k, B, C, D, fin[1]);
         }
         if (k == 0) {
             // rows r-2, r-1 of level 0 are dead now: prefetch rows r+2, r+3 into their registers
@@ -260,7 +273,7 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
     }
 }
 
-template <int T, int MODE, bool VXP, bool VYP>
+template <int T, int MODE, int VXS, int VYS>
 __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_tb(const __grid_constant__ TbArgs a) {
     static_assert(T >= 1 && T <= kTbMaxT, "T out of range");
     const int lane = threadIdx.x & 31;
@@ -328,13 +341,13 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     const int r_end = yb + T;
     for (; r < r_end; r += 4) {
         if (strip_fast && r - T >= a.fy0 && r < a.fy1)
-            tb_tick<T, MODE, VXP, VYP, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
         else
-            tb_tick<T, MODE, VXP, VYP, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
         if (strip_fast && r + 2 - T >= a.fy0 && r + 2 < a.fy1)
-            tb_tick<T, MODE, VXP, VYP, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
         else
-            tb_tick<T, MODE, VXP, VYP, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
     }
 }
 

@@ -1,38 +1,66 @@
-// step_tb_inst.cuh — instantiation helper: each step_tb_inst_<sign>.cu defines one launcher for a
-// fixed pair of upwind directions and switches over (T, MODE) at run time.  Splitting by sign keeps
-// the four translation units compiling in parallel.
+// step_tb_inst.cuh — instantiation helper: each step_inst_<xy>.cu defines one launcher for a fixed
+// pair of upwind selectors (p: v >= 0, n: v < 0, z: v == +0.0 with the term dropped, see tb_update)
+// and switches over (T, MODE) at run time.  Splitting by selector keeps the translation units
+// compiling in parallel.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "step_ring.cuh"
 #include "step_tb.cuh"
 
 namespace csim {
 
-template <bool VXP, bool VYP>
-cudaError_t tb_launch_signed(int T, int mode, const TbArgs& a, cudaStream_t stream) {
+// kind 1: k_step_tb   (two rows per tick, four rows per level — the default);
+// kind 0: k_step_ring (one row per tick, ring of 2T+3 row slots — CSIM_TB_KERNEL=ring)
+template <int VXS, int VYS>
+cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStream_t stream) {
     const dim3 block(32 * kTbWarpsPerBlock);
     const dim3 grid((a.n_items + kTbWarpsPerBlock - 1) / kTbWarpsPerBlock);
-#define CSIM_TB_CASE(TT, MM)                                             \
-    if (T == TT && mode == MM) {                                         \
-        k_step_tb<TT, MM, VXP, VYP><<<grid, block, 0, stream>>>(a);      \
-        return cudaGetLastError();                                       \
+#define CSIM_TB_CASE(TT, MM)                                                  \
+    if (T == TT && mode == MM) {                                              \
+        if (kind == 0)                                                        \
+            k_step_ring<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);     \
+        else                                                                  \
+            k_step_tb<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);       \
+        return cudaGetLastError();                                            \
     }
-    CSIM_TB_CASE(1, MODE_UNIT)
-    CSIM_TB_CASE(2, MODE_UNIT)
-    CSIM_TB_CASE(3, MODE_UNIT)
-    CSIM_TB_CASE(4, MODE_UNIT)
-    CSIM_TB_CASE(1, MODE_RECIP)
-    CSIM_TB_CASE(2, MODE_RECIP)
-    CSIM_TB_CASE(3, MODE_RECIP)
-    CSIM_TB_CASE(4, MODE_RECIP)
-    CSIM_TB_CASE(1, MODE_DIV)
+#define CSIM_RING_CASE(TT, MM)                                                \
+    if (T == TT && mode == MM) {                                              \
+        k_step_ring<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);         \
+        return cudaGetLastError();                                            \
+    }
+    if (VXS != 0 && VYS != 0) {
+        CSIM_TB_CASE(1, MODE_UNIT)
+        CSIM_TB_CASE(2, MODE_UNIT)
+        CSIM_TB_CASE(3, MODE_UNIT)
+        CSIM_TB_CASE(4, MODE_UNIT)
+        CSIM_TB_CASE(1, MODE_RECIP)
+        CSIM_TB_CASE(2, MODE_RECIP)
+        CSIM_TB_CASE(3, MODE_RECIP)
+        CSIM_TB_CASE(4, MODE_RECIP)
+        CSIM_TB_CASE(1, MODE_DIV)
+    } else {
+        // dropped-term variants exist for the blocking depths the loop spends its time in; the few
+        // remainder sweeps (nsteps % T) take the full-arithmetic kernels, which give the same bits
+        CSIM_TB_CASE(3, MODE_UNIT)
+        CSIM_TB_CASE(4, MODE_UNIT)
+        CSIM_TB_CASE(3, MODE_RECIP)
+        CSIM_TB_CASE(4, MODE_RECIP)
+    }
 #undef CSIM_TB_CASE
+#undef CSIM_RING_CASE
     return cudaErrorInvalidValue;
 }
 
-cudaError_t tb_launch_pp(int T, int mode, const TbArgs& a, cudaStream_t stream);
-cudaError_t tb_launch_pn(int T, int mode, const TbArgs& a, cudaStream_t stream);
-cudaError_t tb_launch_np(int T, int mode, const TbArgs& a, cudaStream_t stream);
-cudaError_t tb_launch_nn(int T, int mode, const TbArgs& a, cudaStream_t stream);
+// vxs, vys in {-1, 0, +1}
+cudaError_t tb_launch(int vxs, int vys, int kind, int T, int mode, const TbArgs& a, cudaStream_t stream);
+bool tb_has_zero_variant(int T, int mode);
+
+#define CSIM_DECLARE_LAUNCH(name) \
+    cudaError_t tb_launch_##name(int kind, int T, int mode, const TbArgs& a, cudaStream_t stream);
+CSIM_DECLARE_LAUNCH(pp) CSIM_DECLARE_LAUNCH(pn) CSIM_DECLARE_LAUNCH(np) CSIM_DECLARE_LAUNCH(nn)
+CSIM_DECLARE_LAUNCH(pz) CSIM_DECLARE_LAUNCH(nz) CSIM_DECLARE_LAUNCH(zp) CSIM_DECLARE_LAUNCH(zn)
+CSIM_DECLARE_LAUNCH(zz)
+#undef CSIM_DECLARE_LAUNCH
 
 }  // namespace csim

@@ -184,6 +184,14 @@ double csim_safe_dt(double dx, double dy, double vx, double vy, double D);
 /* Device-side stability diagnostic (not in the reference; north_star's "CFL check as a
  * warp-shuffle reduction"): max |u| over the interior and count of non-finite cells. */
 int csim_field_health(const csim_field* f, double* max_abs, uint64_t* nonfinite);
+/* What the library currently knows about the values of the tile: 0 unknown (written from outside the
+ * fused step since the last scan), 1 clean (every cell of the padded tile finite, below 2^1000 in
+ * magnitude and not -0.0), 2 tainted (a scan found such a cell).  When a velocity component is exactly
+ * +0.0, csim_step_fused / csim_run_steps scan an unknown tile once and, on clean tiles with a monotone
+ * time step (dt*(2D(1/dx^2+1/dy^2)+|vx|/dx+|vy|/dy) <= 1), skip that component's advection term —
+ * bit-identical there (DESIGN.md "dropped zero-velocity terms"), 3 of 14 FP64 operations per cell
+ * fewer.  Any other tile runs the full arithmetic.  CSIM_ZERO_TERMS=0 in the environment disables it. */
+int csim_field_value_state(const csim_field* f);
 
 /* ---- decomposition: include/decomp.hpp:4-17, src/decomp.cpp:5-39 --------------------------- */
 

@@ -287,6 +287,77 @@ def test_full_size_windows_and_linearity(csim, ctx, oracle_mod, port, n):
     assert np.all(u.download_interior() == 3.141592653589793)
 
 
+# ---- dropped zero-velocity terms (csim_field_value_state) ------------------------------
+
+def plateau_tile(rng, ny, nx, negzero=False):
+    """Random tile with flat patches (zero differences → signed-zero arithmetic in the advection term),
+    exact +0.0 cells and, optionally, -0.0 cells (which must send the run to the full arithmetic)."""
+    a = rand_tile(rng, ny, nx)
+    for _ in range(12):
+        y, x = rng.integers(0, ny), rng.integers(0, nx)
+        a[y:y + rng.integers(2, 9), x:x + rng.integers(2, 9)] = rng.choice([0.0, 1.5, -2.25, 1e-300])
+    a[rng.random(a.shape) < 0.02] = 0.0
+    if negzero:
+        a[rng.random(a.shape) < 0.02] = -0.0
+        y, x = ny // 2, nx // 2
+        a[y:y + 6, x:x + 6] = -0.0  # a patch: c == -0 with o == -0 is the one case that differs
+    return a
+
+
+@pytest.mark.parametrize("vx,vy,D", [(0.5, 0.0, 0.05), (-0.4, 0.0, 0.05), (0.0, 0.3, 0.05), (0.0, -0.3, 0.0),
+                                     (0.0, 0.0, 0.05), (0.5, 0.0, 0.0)])
+def test_zero_velocity_terms_are_exact(csim, ctx, oracle_mod, port, vx, vy, D):
+    rng = np.random.default_rng(int(1000 * abs(vx) + 100 * abs(vy)) + 3)
+    T = csim.steps_per_sweep()
+    steps = 2 * T + 1  # two full-depth sweeps (dropped-term kernels) + a remainder (full arithmetic)
+    for (ny, nx), bc in (((130, 257), (2, 2, 2, 2)), ((64, 300), (0, 1, 2, 1)), ((257, 140), (1, 0, 1, 0))):
+        for negzero in (False, True):
+            u0 = plateau_tile(rng, ny, nx, negzero)
+            sp = oracle_mod.SimParams(nx=nx, ny=ny, D=D, vx=vx, vy=vy, dt=0.1, steps=steps, out_every=steps, bc=bc)
+            want = port.run(sp, u0_padded=u0)["final"]
+            u, tmp = make_fields(csim, ctx, u0)
+            dec = csim.Decomp2D.single(nx, ny)
+            B = csim.BCType
+            p = csim.make_step_params(D, vx, vy, 0.1, csim.BCConfig(*[B(b) for b in bc]), dec)
+            assert u.value_state == 0
+            csim.run_steps(u, tmp, p, dec, steps)
+            assert bits_equal(u.download_interior(), want), (ny, nx, bc, negzero)
+            if T >= 3:  # the scan ran and classified the tile; clean tiles took the dropped-term kernels
+                assert u.value_state == (2 if negzero else 1)
+
+
+def test_zero_velocity_terms_fallbacks(csim, ctx, oracle_mod, port):
+    """Non-monotone time step, -0.0 velocity, non-finite cell: all must run the full arithmetic and
+    match the reference bit for bit (NaN payloads aside, none arise here)."""
+    rng = np.random.default_rng(77)
+    ny, nx, steps = 96, 260, 7
+    dec = csim.Decomp2D.single(nx, ny)
+    P = csim.BCType.Periodic
+    for (D, vx, vy, dt) in ((0.2, 0.5, 0.0, 1.0),     # dt*(2D*2+|vx|) = 1.3 > 1 although dt <= safe_dt
+                            (0.05, 0.5, -0.0, 0.1)):  # -0.0 selects the backward difference AND flips the zero's sign
+        u0 = plateau_tile(rng, ny, nx)
+        sp = oracle_mod.SimParams(nx=nx, ny=ny, D=D, vx=vx, vy=vy, dt=dt, steps=steps, out_every=steps, bc=(2, 2, 2, 2))
+        want = port.run(sp, u0_padded=u0)["final"]
+        u, tmp = make_fields(csim, ctx, u0)
+        p = csim.make_step_params(D, vx, vy, dt, csim.BCConfig(P, P, P, P), dec)
+        csim.run_steps(u, tmp, p, dec, steps)
+        assert bits_equal(u.download_interior(), want), (D, vx, vy, dt)
+        assert u.value_state != 1 or vy != 0.0 or dt < 1.0
+    u0 = plateau_tile(rng, ny, nx)
+    u0[40, 100] = np.inf
+    u, tmp = make_fields(csim, ctx, u0)
+    p = csim.make_step_params(0.05, 0.5, 0.0, 0.1, csim.BCConfig(P, P, P, P), dec)
+    T = csim.steps_per_sweep()
+    csim.run_steps(u, tmp, p, dec, T)
+    assert u.value_state == 2 or T < 3
+    sp = oracle_mod.SimParams(nx=nx, ny=ny, D=0.05, vx=0.5, vy=0.0, dt=0.1, steps=T, out_every=T, bc=(2, 2, 2, 2))
+    want = port.run(sp, u0_padded=u0)["final"]
+    got = u.download_interior()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+    ok = np.isfinite(want)
+    assert bits_equal(got[ok], want[ok])
+
+
 # ---- reductions ----------------------------------------------------------------------------------
 
 def test_minmax_and_health(csim, ctx):

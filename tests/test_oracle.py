@@ -215,3 +215,64 @@ def test_periodic_equals_dirichlet_zero(oracle_mod, port):
     a = port.run(oracle_mod.SimParams(nx=40, ny=40, D=0.05, vx=0.5, steps=50, out_every=50, bc=(2, 2, 2, 2)))
     b = port.run(oracle_mod.SimParams(nx=40, ny=40, D=0.05, vx=0.5, steps=50, out_every=50, bc=(0, 0, 0, 0)))
     assert bits_equal(a["final"], b["final"])
+
+
+# ---- signed zeros and zero velocities: the regime behind the dropped-term kernels -----------------
+
+def _signed_zero_tile(rng, ny, nx, negzero):
+    a = rng.standard_normal((ny + 2, nx + 2)) * 10.0 ** rng.integers(-3, 3, (ny + 2, nx + 2))
+    for _ in range(10):
+        y, x = rng.integers(0, ny), rng.integers(0, nx)
+        a[y:y + rng.integers(2, 9), x:x + rng.integers(2, 9)] = rng.choice([0.0, 1.5, -2.25, 1e-300])
+    a[rng.random(a.shape) < 0.03] = 0.0
+    if negzero:
+        a[rng.random(a.shape) < 0.03] = -0.0
+        a[ny // 2:ny // 2 + 6, nx // 2:nx // 2 + 6] = -0.0
+    return a
+
+
+def test_port_equals_reference_objects_on_signed_zero_fields(oracle_mod, port, ref):
+    """Pins the port where the GPU's zero-velocity tests use it: flat patches, +0.0 / -0.0 cells,
+    velocity components that are +0.0 or -0.0."""
+    rng = np.random.default_rng(2024)
+    for (vx, vy, D) in ((0.5, 0.0, 0.05), (0.0, -0.3, 0.0), (0.0, 0.0, 0.05), (0.5, -0.0, 0.05)):
+        for negzero in (False, True):
+            u0 = _signed_zero_tile(rng, 40, 70, negzero)
+            sp = oracle_mod.SimParams(nx=70, ny=40, D=D, vx=vx, vy=vy, dt=0.1, steps=7, out_every=7, bc=(0, 1, 2, 1))
+            a = port.run(sp, u0_padded=u0)["final"]
+            b = ref.run(sp, u0_padded=u0)["final"]
+            assert bits_equal(a, b), (vx, vy, D, negzero)
+
+
+def _np_update(c, w, e, s, n, dtD, ndt, vx, vy, drop_x=False, drop_y=False):
+    """numpy restatement of tb_update (MODE_UNIT; numpy never contracts into FMA; e - 2c has one
+    rounding either way)."""
+    o = c + dtD * (((e - 2.0 * c) + w) + ((n - 2.0 * c) + s))
+    if drop_x and drop_y:
+        return o
+    px = vx * ((c - w) if vx >= 0 else (e - c))
+    py = vy * ((c - s) if vy >= 0 else (n - c))
+    adv = py if drop_x else (px if drop_y else px + py)
+    return o + ndt * adv
+
+
+def test_dropped_zero_velocity_term_is_exact_without_negative_zero():
+    """The claim the dispatcher (kernels.cu, resolve_zero_terms) relies on, checked with IEEE arithmetic
+    on the host: for finite cells without -0.0, dropping the term of a +0.0 velocity component does
+    not change a single bit; with -0.0 cells it can (which is why such tiles take the full kernels)."""
+    rng = np.random.default_rng(5)
+    differs_with_negzero = False
+    for negzero in (False, True):
+        a = _signed_zero_tile(rng, 200, 300, negzero)
+        c, w, e, s, n = a[1:-1, 1:-1], a[1:-1, :-2], a[1:-1, 2:], a[:-2, 1:-1], a[2:, 1:-1]
+        for (vx, vy, D) in ((0.5, 0.0, 0.05), (-0.5, 0.0, 0.05), (0.0, 0.25, 0.05), (0.0, -0.25, 0.0), (0.0, 0.0, 0.05)):
+            full = _np_update(c, w, e, s, n, 0.1 * D, -0.1, vx, vy)
+            drop = _np_update(c, w, e, s, n, 0.1 * D, -0.1, vx, vy, drop_x=(vx == 0.0), drop_y=(vy == 0.0))
+            if negzero:
+                differs_with_negzero |= not bits_equal(full, drop)
+                ok = np.signbit(c) & (c == 0.0)  # differences may only sit on -0.0 centre cells
+                assert bits_equal(full[~ok], drop[~ok])
+            else:
+                assert bits_equal(full, drop), (vx, vy, D)
+                assert not np.any(np.signbit(full) & (full == 0.0))  # and no -0.0 is ever created
+    assert differs_with_negzero
