@@ -277,6 +277,60 @@ def run_ours(args):
     ms_e2e, _ = timed(window_e2e, max(2, min(args.steps, 3)), 1)
     e2e_steps = max(2, min(args.steps, 3))
 
+    # The same end-to-end window with THREE windows in flight (one GPU only): extra contexts with their
+    # own stream, tiles and pinned buffers, so that one window's PCIe copies (H2D before, D2H after its
+    # 100 steps) overlap the other window's sweeps.  Every window still pays its own H2D and D2H inside
+    # the timed region; only the overlap is new.  This is the throughput a caller with independent
+    # members to advance (an ensemble) gets from the same C-ABI calls.
+    ms_pipe, pipe_steps, n_lanes = None, 0, 3
+    if world == 1:
+        lanes = [(ctx, u, tmp, host_in, host_out)]
+        for _ in range(n_lanes - 1):
+            c2 = csim.Context(local_rank)
+            hin2 = c2.pinned_empty(host_in.shape)
+            hin2[:] = host_in
+            lanes.append((c2, csim.Field(c2, dec.nx_local, dec.ny_local, 1, 1.0, 1.0),
+                          csim.Field(c2, dec.nx_local, dec.ny_local, 1, 1.0, 1.0), hin2,
+                          c2.pinned_empty(host_out.shape)))
+        per_lane = max(2, min(args.steps, 4))
+        pipe_steps = n_lanes * per_lane
+        errors = []
+
+        def lane_loop(lane, count):
+            # one host thread per lane: a lane blocks in its own context (value scan after the upload,
+            # final sync) without holding up the others; ctypes releases the GIL during the calls
+            c, uu, tt, hin, hout = lane
+            try:
+                for _ in range(count):
+                    uu.upload_async(hin)
+                    csim.run_steps(uu, tt, params, dec, inner)
+                    uu.download_interior_async(hout)
+                    c.sync()  # the frame is on the host
+            except Exception as exc:  # noqa: BLE001
+                errors.append(exc)
+
+        def run_lanes(count):
+            ths = [threading.Thread(target=lane_loop, args=(lane, count)) for lane in lanes]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errors:
+                raise errors[0]
+
+        run_lanes(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_lanes(per_lane)
+        torch.cuda.synchronize()
+        ms_pipe = 1e3 * (time.perf_counter() - t0)  # several streams: wall clock around a full drain
+        for lane in lanes[1:]:
+            if not np.array_equal(host_out, lane[4]):
+                raise SystemExit("bench.py: the pipelined lanes disagree")
+            lane[1].close()
+            lane[2].close()
+            lane[0].close()
+
     cells_per_window = float(nxg) * float(nyg) * inner
     value = cells_per_window * args.steps / (ms * 1e-3)
     e2e_value = cells_per_window * e2e_steps / (ms_e2e * 1e-3)
@@ -335,9 +389,19 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (two 537 MB fields per GPU vs 126 MB L2); no flush needed"
                        if tile >= 4096 else "WARNING: fields fit in L2"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "e2e": ({"value": cells_per_window * pipe_steps / (ms_pipe * 1e-3), "unit": "cell-updates/s",
+                     "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
+                     "steps": pipe_steps, "ms_per_step": ms_pipe / pipe_steps,
+                     "mode": f"{n_lanes} windows in flight (one context each on the GPU): every window's H2D and D2H are "
+                             "inside the timed region and overlap the other windows' sweeps; one host thread per window "
+                             "lane; host wall clock around a full drain",
+                     "serial": {"value": e2e_value, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                                "mode": "one window at a time: H2D, 100 steps, D2H, sync"}}
+                    if ms_pipe else
+                    {"value": e2e_value, "unit": "cell-updates/s",
+                     "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
+                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                     "mode": "one window at a time per rank: H2D, 100 steps, D2H, sync"}),
             "all_terms": {"value": gen_value, "unit": "cell-updates/s", "vx": -0.5, "vy": 0.25, "steps": gen_steps,
                           "note": "same window with both velocity components non-zero (14 FP64 ops per cell)"},
             "gpu_launches": launches, "clocks": clocks,

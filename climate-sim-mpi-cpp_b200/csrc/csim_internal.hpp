@@ -95,10 +95,9 @@ bool tb_split_pointless(int nchunks, int n_int);
 // kernels.cu
 int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mode);
 // May the sweep drop the advection term of a velocity component that is exactly +0.0 (tb_update)?
-// Scans `u` if its state is unknown; with `collective` every rank of the communicator must call it
-// (one MAX reduction makes the answer the same everywhere).
+// Scans `u` if its state is unknown (one pass + host sync, once per upload).
 int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k, int mode, int maxT,
-                       bool collective, bool* allowed);
+                       bool* allowed);
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
                    int T, int part, cudaStream_t stream, bool* launched, bool zero_terms = false);
 

@@ -602,10 +602,10 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     //               before the frame's event arrives and the frame waits a whole round for slots:
     //               measured chain frame-wait 88 + frame 88 + exchange 132 us = 308 us per block
     //               against 285 us of work (profiles/r01_multigpu_phases.md).
-    // one decision for the whole call, the same on every rank (csim_run_steps is collective)
+    // one decision for the whole call, taken per rank (see resolve_zero_terms)
     bool zero_terms = false;
     if (nsteps >= maxT)
-        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, true, &zero_terms)) return rc;
+        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, &zero_terms)) return rc;
     const int values_after = zero_terms ? csim_field::kClean
                                         : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
     const bool p2p = peer_path_enabled(c, u, tmp);

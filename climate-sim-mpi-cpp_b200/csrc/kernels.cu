@@ -367,11 +367,16 @@ bool tb_has_zero_variant(int T, int mode) { return (T == 3 || T == 4) && (mode =
 //   (2) the field stays finite                                                → the step is a convex
 //       combination of the five cells when dt*(2D(1/dx²+1/dy²) + |vx|/dx + |vy|/dy) <= 1 (max
 //       principle; the scan bounds |u| by 2^1000, so rounding cannot carry it to overflow), and
-//   (3) every rank decides alike (halo cells are advanced redundantly on both sides of an edge).
-// Anything else — a tainted tile, a non-monotone step, a -0.0 or negative-zero velocity — runs the
-// full arithmetic.
+// Anything else — a tainted tile, a non-monotone step, a -0.0 velocity — runs the full arithmetic.
+// Multi-rank runs decide per rank, without a collective (a host-synchronous reduction per call would
+// drain the launch queue: measured 7.1 → 8.0 ms per 100 steps on 2 GPUs).  That is sound for (1)'s
+// -0.0 half: the halo cells a rank advances redundantly are only ever NEIGHBOURS of its own cells,
+// and the sign of a zero neighbour cannot change a result whose centre is not -0.0.  It leaves one
+// gap, stated in DESIGN.md: a non-finite value that enters a clean rank's halo from a tainted
+// neighbour meets 0*inf = NaN in the reference but not here, so WHICH cells turn NaN next to a
+// blow-up front may differ across a rank boundary.  Finite fields are bit-identical.
 int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k, int mode, int maxT,
-                       bool collective, bool* allowed) {
+                       bool* allowed) {
     *allowed = false;
     static const bool off = tb_env_int("CSIM_ZERO_TERMS", 1) == 0;
     const bool candidate = !off && tb_has_zero_variant(maxT, mode) && (is_pos_zero(k.vx) || is_pos_zero(k.vy));
@@ -398,13 +403,7 @@ int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k,
         std::memcpy(&bad, c->h_scratch, sizeof bad);
         u->values = bad ? csim_field::kTainted : csim_field::kClean;
     }
-    ok = ok && u->values == csim_field::kClean;
-    if (collective) {
-        double veto = ok ? 0.0 : 1.0;
-        if (int rc = csim_comm_allreduce_max(c, &veto, 1)) return rc;
-        ok = veto == 0.0;
-    }
-    *allowed = ok;
+    *allowed = ok && u->values == csim_field::kClean;
     return CSIM_OK;
 }
 
@@ -510,6 +509,36 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.nchunks = (rows + ch - 1) / ch;
     const int eh = (ch + a.edge_split - 1) / a.edge_split;
     const int nch_edge = (rows + eh - 1) / eh;
+    // Tail of the launch.  With uniform chunks the last, partly filled round of resident warps costs
+    // a whole chunk time (3.44 rounds at 8192^2: SMs active 93 % of the launch).  Chunks that fill
+    // whole rounds keep the full height; the rows left over are cut into shorter chunks, which are
+    // enumerated last.  The geometry does not depend on `part`: interior and frame launches of one
+    // block must cover every chunk exactly once.
+    a.n_main = a.nchunks;
+    a.chunk_h2 = ch;
+    static const int tail_on = tb_env_int("CSIM_TB_TAIL", 1);
+    if (tail_on && n_int > 0) {
+        const long long edge_items = static_cast<long long>(n_edge) * nch_edge;
+        const long long items_uniform = edge_items + static_cast<long long>(a.nchunks) * n_int;
+        const long long full_rounds = items_uniform / slots;
+        long long best = ((items_uniform + slots - 1) / slots) * (ch + 2 * T);
+        long long n_main = (full_rounds * slots - edge_items) / n_int;
+        if (n_main > a.nchunks) n_main = a.nchunks;
+        if (full_rounds >= 1 && n_main >= 1 && n_main * ch < rows) {
+            const long long rest = rows - n_main * ch;
+            for (int div = 2; div <= 4; ++div) {
+                const int h2 = ch / div < 16 ? 16 : ch / div;
+                const long long n_small = (rest + h2 - 1) / h2;
+                const long long cost = full_rounds * (ch + 2 * T) + ((n_small * n_int + slots - 1) / slots) * (h2 + 2 * T);
+                if (cost < best) {
+                    best = cost;
+                    a.n_main = static_cast<int>(n_main);
+                    a.chunk_h2 = h2;
+                    a.nchunks = static_cast<int>(n_main + n_small);
+                }
+            }
+        }
+    }
     a.int_chunk0 = 0;
     a.frame_pair = 0;
     int int_chunks = a.nchunks;
@@ -659,7 +688,7 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     static const bool debug_split = tb_env_int("CSIM_DEBUG_SPLIT", 0) != 0;
     bool zero_terms = false;
     if (nsteps >= maxT)
-        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, false, &zero_terms)) return rc;
+        if (int rc = resolve_zero_terms(u, p, k, mode, maxT, &zero_terms)) return rc;
     const int values_after = zero_terms ? csim_field::kClean
                                         : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
     int left = nsteps;

@@ -116,10 +116,12 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kRingBlocksPerSM) k_ste
         } else {
             const int e = item - a.n_edge_items;
             strip = 1 + e % n_int;
-            h = a.chunk_h;
             const int ci = e / n_int;
             const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
-            ya = a.sy0 + chunk * h;
+            // the first n_main chunks are chunk_h rows tall, the rest (the tail of the launch) chunk_h2
+            const bool tail = chunk >= a.n_main;
+            h = tail ? a.chunk_h2 : a.chunk_h;
+            ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
         }
     }
     if (ya >= a.sy1) return;

@@ -51,6 +51,8 @@ struct TbArgs {
     int nstrips;       // strips across x
     int nchunks;       // chunks down y for interior strips
     int chunk_h;       // rows per chunk (interior strips); edge strips use chunk_h / edge_split
+    int n_main;        // interior strips: chunks 0 … n_main-1 are chunk_h rows tall,
+    int chunk_h2;      // chunks n_main … nchunks-1 are chunk_h2 rows tall (finer grain for the last round)
     int edge_split;
     int n_items;       // total (strip, chunk) work items of this launch
     int n_edge_items;  // of which the first n_edge_items belong to the edge strips (0: none in this launch)
@@ -294,10 +296,12 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
         } else {
             const int e = item - a.n_edge_items;
             strip = 1 + e % n_int;
-            h = a.chunk_h;
             const int ci = e / n_int;
             const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
-            ya = a.sy0 + chunk * h;
+            // the first n_main chunks are chunk_h rows tall, the rest (the tail of the launch) chunk_h2
+            const bool tail = chunk >= a.n_main;
+            h = tail ? a.chunk_h2 : a.chunk_h;
+            ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
         }
     }
     if (ya >= a.sy1) return;
