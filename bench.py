@@ -191,6 +191,8 @@ def run_ours(args):
     tile, inner = args.tile, args.inner
     dims = csim.Decomp2D.init(world, 0, 1, 1).dims
     nxg, nyg = tile * dims[0], tile * dims[1]
+    if args.global_size:  # strong scaling (configs[3]): the global grid is fixed, tiles shrink with N
+        nxg = nyg = args.global_size
     dec = csim.Decomp2D.init(world, rank, nxg, nyg)
     if world > 1:
         box = [csim.comm_unique_id() if rank == 0 else None]
@@ -198,7 +200,11 @@ def run_ours(args):
         ctx.comm_init(world, rank, box[0])
 
     P = csim.BCType.Periodic
-    params = csim.make_step_params(PHYS["D"], PHYS["vx"], PHYS["vy"], PHYS["dt"], csim.BCConfig(P, P, P, P), dec)
+    bcs = csim.BCConfig(P, P, P, P)
+    if args.bc == "dn":  # configs[3]: Dirichlet and Neumann sides
+        Dn, Nn = csim.BCType.Dirichlet, csim.BCType.Neumann
+        bcs = csim.BCConfig(Dn, Nn, Dn, Nn)
+    params = csim.make_step_params(PHYS["D"], PHYS["vx"], PHYS["vy"], PHYS["dt"], bcs, dec)
     host_in = ctx.pinned_empty((dec.ny_local + 2, dec.nx_local + 2))
     host_in[:] = 0.0
     csim.initial_condition_host(dec, 1, 1.0, 1.0, out=host_in)
@@ -208,8 +214,11 @@ def run_ours(args):
     u.upload(host_in)
     halo_path = "none"
     if world > 1:
-        halo_path = "nccl"
-        if os.environ.get("CSIM_HALO", "p2p") != "nccl":
+        # default: T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block over NVLink,
+        # hidden behind the interior sweep.  CSIM_HALO=p2p selects the peer-memory push instead, which
+        # measured slower with the round-1b kernel (profiles/r01b_weak_scaling.md).
+        halo_path = "pack + grouped NCCL send/recv over NVLink + unpack, overlapped with the interior sweep"
+        if os.environ.get("CSIM_HALO", "nccl") == "p2p":
             csim.peer_setup(u, tmp, dec)  # neighbours' tiles mapped over CUDA IPC: direct NVLink stores
             halo_path = "peer-memory push (CUDA IPC over NVLink) + flag, NCCL only for bootstrap"
 
@@ -267,15 +276,17 @@ def run_ours(args):
     # with both velocity components non-zero and negative vx as well, so the full arithmetic and the
     # forward-difference branches are on record next to the headline.
     dropped = u.value_state == 1 and (PHYS["vx"] == 0.0 or PHYS["vy"] == 0.0) and csim.steps_per_sweep() >= 3
-    gen_params = csim.make_step_params(PHYS["D"], -0.5, 0.25, PHYS["dt"], csim.BCConfig(P, P, P, P), dec)
+    gen_params = csim.make_step_params(PHYS["D"], -0.5, 0.25, PHYS["dt"], bcs, dec)
 
     def window_general():
         csim.run_steps(u, tmp, gen_params, dec, inner)
 
     gen_steps = max(2, min(args.steps, 5))
     ms_gen, _ = timed(window_general, gen_steps, 1)
-    ms_e2e, _ = timed(window_e2e, max(2, min(args.steps, 3)), 1)
     e2e_steps = max(2, min(args.steps, 3))
+    ms_e2e = None
+    if not args.no_e2e:
+        ms_e2e, _ = timed(window_e2e, e2e_steps, 1)
 
     # The same end-to-end window with THREE windows in flight (one GPU only): extra contexts with their
     # own stream, tiles and pinned buffers, so that one window's PCIe copies (H2D before, D2H after its
@@ -283,7 +294,7 @@ def run_ours(args):
     # the timed region; only the overlap is new.  This is the throughput a caller with independent
     # members to advance (an ensemble) gets from the same C-ABI calls.
     ms_pipe, pipe_steps, n_lanes = None, 0, 3
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         lanes = [(ctx, u, tmp, host_in, host_out)]
         for _ in range(n_lanes - 1):
             c2 = csim.Context(local_rank)
@@ -333,7 +344,7 @@ def run_ours(args):
 
     cells_per_window = float(nxg) * float(nyg) * inner
     value = cells_per_window * args.steps / (ms * 1e-3)
-    e2e_value = cells_per_window * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = cells_per_window * e2e_steps / (ms_e2e * 1e-3) if ms_e2e else None
     gen_value = cells_per_window * gen_steps / (ms_gen * 1e-3)
 
     # sanity: the field must still be finite and must have moved (the work was really done)
@@ -361,11 +372,14 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"csim::k_step_tb<T={T}> (fused diffusion+advection sweep, {T} steps per launch)",
+                "traffic": traffic, "kernel": f"csim::k_step_tb<T={T}> (fused diffusion+advection sweep, {T} steps per launch"
+                                              + (", y-advection term dropped: vy == +0.0)" if dropped else ")"),
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": launch_ms,
                 "steps_per_launch": steps_per_launch, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "note": "algorithmic bytes = 16 B per cell update; temporal blocking moves 16/T B per update "
-                        "through HBM, so frac > 1 is expected and the kernel is FP64-pipe-bound (DESIGN.md 4.1)"}
+                        "through HBM, so frac > 1 is expected; measured DRAM traffic per launch is in `traffic`; at "
+                        "T = 3 the kernel runs the FP64 pipe at ~74 % and HBM at ~79 % of the measured peak "
+                        "(DESIGN.md 4.1)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -379,9 +393,14 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_size else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(tile, dims), "timesteps_per_step": inner,
+            "config": {"workload": workload_name(tile, dims) if not args.global_size else
+                       (f"{nxg}x{nyg} global (strong scaling), Gaussian hotspot, diffusion+advection, BCs left/bottom "
+                        f"Dirichlet, right/top Neumann, decomp {{{dims[0]},{dims[1]}}}, tile {dec.nx_local}x{dec.ny_local}"
+                        if args.bc == "dn" else f"{nxg}x{nyg} global (strong scaling), periodic BCs, decomp {{{dims[0]},{dims[1]}}}"),
+                       "timesteps_per_step": inner,
                        "parallelism": f"cartesian {dims[0]}x{dims[1]}, 1 rank per GPU", "halo_exchange": halo_path,
                        "physics": dict(PHYS),
                        "arithmetic": ("vy == +0.0 on a scanned-clean field: y-advection term dropped, 11 FP64 ops per "
@@ -397,7 +416,7 @@ def run_ours(args):
                              "lane; host wall clock around a full drain",
                      "serial": {"value": e2e_value, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                                 "mode": "one window at a time: H2D, 100 steps, D2H, sync"}}
-                    if ms_pipe else
+                    if ms_pipe else None if ms_e2e is None else
                     {"value": e2e_value, "unit": "cell-updates/s",
                      "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
                      "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
@@ -426,6 +445,11 @@ def main():
     ap.add_argument("--inner", type=int, default=100, help="time steps per bench step (output window)")
     ap.add_argument("--ref-inner", type=int, default=4, help="time steps per bench step for the CPU reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end windows (profiling runs)")
+    ap.add_argument("--global-size", type=int, default=0,
+                    help="strong scaling: fixed NxN global grid split over the ranks (32768 = configs[3])")
+    ap.add_argument("--bc", choices=["periodic", "dn"], default="periodic",
+                    help="dn: left/bottom Dirichlet, right/top Neumann (configs[3])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"bench.py: note: warmup {args.warmup} < 3", file=sys.stderr)

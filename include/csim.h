@@ -232,7 +232,9 @@ int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
  * process).  csim_run_steps then replaces pack → NCCL → unpack by ONE kernel whose CTAs store this
  * rank's edge bands straight into the neighbours' ghost lines over NVLink and raise a flag there; the
  * neighbour's frame sweep is gated by a bounded wait on that flag (CSIM_ERR_TIMEOUT, never a hang).
- * Without this call, or with CSIM_HALO=nccl in the environment, the NCCL path is used.
+ * Without this call, or with CSIM_HALO=nccl in the environment, the NCCL path is used — which is what
+ * bench.py and the C++ drop-in do by default: with the round-1b sweep the NCCL path measured faster at
+ * 2, 4 and 8 GPUs (profiles/r01b_weak_scaling.md); CSIM_HALO=p2p opts into this path there.
  * Call csim_peer_teardown on every rank (after a barrier) before destroying the tiles; destroying a
  * mapped tile also takes this rank's links down. */
 int csim_peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec);
