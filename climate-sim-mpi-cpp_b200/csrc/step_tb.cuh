@@ -235,7 +235,7 @@ __device__ __forceinline__ void tb_store_row(const TbArgs& a, const TbLane& ln, 
 // and no register is ever moved.
 template <int T, int MODE, int VXS, int VYS, int PH, bool GEN>
 __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int lane, bool lane_store_all,
-                                        bool can_load, int r, int ya, int yb, const double*& src,
+                                        bool can_load, int r, int ya, int yb, const double*& src, double*& dst,
                                         double (&st)[T][2][2][4]) {
     double fin[2][4];
 #pragma unroll
@@ -252,13 +252,16 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
             tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k, B, C, D, fin[1]);
         }
         if (k == 0) {
-            // rows r-2, r-1 of level 0 are dead now: prefetch rows r+2, r+3 into their registers
-            tb_load4(src, can_load, A);
-            tb_load4(src + a.pitch, can_load, B);
+            // rows r-2, r-1 of level 0 are dead now: prefetch rows r+2, r+3 into their registers.
+            // Fast ticks run only in strips that lie inside the row allocation with all 32 lanes
+            // (strip_fast implies xb + 128 <= nx + T < xmax_load), so their loads are unconditional.
+            const bool ld = GEN ? can_load : true;
+            tb_load4(src, ld, A);
+            tb_load4(src + a.pitch, ld, B);
             // pull the rows pf_rows ahead into L2 (costs no registers; clamped to the allocation)
-            if (can_load && r + 3 + a.pf_rows < a.row_limit) {
-                tb_prefetch_l2(src + static_cast<long long>(a.pf_rows) * a.pitch);
-                tb_prefetch_l2(src + static_cast<long long>(a.pf_rows + 1) * a.pitch);
+            if (ld && r + 3 + a.pf_rows < a.row_limit) {
+                tb_prefetch_l2(src + a.pf_off);
+                tb_prefetch_l2(src + a.pf_off + a.pitch);
             }
             src += 2 * a.pitch;
         }
@@ -266,13 +269,13 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
     if (!GEN) {
         // fast ticks run only in strips where every lane stores all four cells or none, and the rows
         // they finish are interior rows: one predicated 256-bit store per row, no per-cell tests
-        double* dst = a.out + static_cast<long long>(r - T) * a.pitch + ln.x0;
         if (lane_store_all && r - T >= ya && r - T < yb) tb_store4(dst, fin[0]);
         if (lane_store_all && r - T + 1 >= ya && r - T + 1 < yb) tb_store4(dst + a.pitch, fin[1]);
     } else {
         tb_store_row(a, ln, lane, lane_store_all, r - T, ya, yb, fin[0]);
         tb_store_row(a, ln, lane, lane_store_all, r - T + 1, ya, yb, fin[1]);
     }
+    dst += 2 * a.pitch;  // row r-T of `out` at this lane's columns, kept incrementally like src
 }
 
 template <int T, int MODE, int VXS, int VYS>
@@ -340,18 +343,19 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     tb_load4(src, can_load, st[0][1][0]);
     tb_load4(src + a.pitch, can_load, st[0][1][1]);
     src += 2 * a.pitch;
+    double* dst = a.out + static_cast<long long>(r - T) * a.pitch + ln.x0;  // first tick finishes rows r-T, r-T+1
 
     // every tick touches rows r-T .. r+1; it is "fast" when all rows it produces are interior
     const int r_end = yb + T;
     for (; r < r_end; r += 4) {
         if (strip_fast && r - T >= a.fy0 && r < a.fy1)
-            tb_tick<T, MODE, VXS, VYS, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, dst, st);
         else
-            tb_tick<T, MODE, VXS, VYS, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, dst, st);
         if (strip_fast && r + 2 - T >= a.fy0 && r + 2 < a.fy1)
-            tb_tick<T, MODE, VXS, VYS, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, dst, st);
         else
-            tb_tick<T, MODE, VXS, VYS, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, dst, st);
     }
 }
 
