@@ -40,6 +40,16 @@ __global__ void k_fill(double* __restrict__ p, int64_t n, double v) {
         p[k] = v;
 }
 
+// Row-wise copy between two device arrays of different pitch (doubles): the device half of the
+// staged host transfers below (dense host layout <-> pitched tile).
+__global__ void __launch_bounds__(256) k_repitch(const double* __restrict__ src, int64_t spitch,
+                                                 double* __restrict__ dst, int64_t dpitch, int width, int height) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= width) return;
+    for (int y = blockIdx.y; y < height; y += gridDim.y)
+        dst[static_cast<int64_t>(y) * dpitch + x] = src[static_cast<int64_t>(y) * spitch + x];
+}
+
 // Interior of the pitched tile → dense ny x nx array of big-endian doubles (NetCDF wire order).
 __global__ void __launch_bounds__(256) k_pack_interior_be(const double* __restrict__ in, int nx, int ny,
                                                           int64_t pitch, unsigned long long* __restrict__ out) {
@@ -128,6 +138,7 @@ int csim_ctx_destroy(csim_ctx* c) {
     if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_wide) cudaFree(c->d_wide);
     if (c->d_snap) cudaFree(c->d_snap);
+    if (c->d_stage) cudaFree(c->d_stage);
     delete c;
     return CSIM_OK;
 }
@@ -241,6 +252,26 @@ static int copy2d(const csim_field* f, void* dst, size_t dpitch, const void* src
     return CSIM_OK;
 }
 
+// Large asynchronous transfers go through a dense device staging buffer: ONE contiguous DMA plus a
+// re-pitch kernel instead of cudaMemcpy2DAsync, whose per-row descriptors (8194 of them for an 8192²
+// tile) kept the calling thread inside the driver for most of the copy and thereby held up every other
+// host thread's CUDA calls (tools/e2e_timeline.py: a lane's H2D was issued only after another lane's
+// D2H had finished).
+static constexpr size_t kStagedMinBytes = size_t(4) << 20;
+static int ensure_stage(csim_ctx* c, size_t doubles) {
+    if (c->stage_doubles >= doubles) return CSIM_OK;
+    if (c->d_stage) {
+        CSIM_CUDA(cudaStreamSynchronize(c->stream));
+        CSIM_CUDA(cudaFree(c->d_stage));
+        c->d_stage = nullptr;
+        c->stage_doubles = 0;
+    }
+    CSIM_CUDA(cudaMalloc(&c->d_stage, doubles * sizeof(double)));
+    c->stage_doubles = doubles;
+    return CSIM_OK;
+}
+static dim3 repitch_grid(int width, int height) { return dim3((width + 255) / 256, height < 2048 ? height : 2048); }
+
 int csim_field_upload(csim_field* f, const double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload: null argument");
     f->values = csim_field::kUnknown;
@@ -250,6 +281,16 @@ int csim_field_upload(csim_field* f, const double* host) {
 int csim_field_upload_async(csim_field* f, const double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_upload_async: null argument");
     f->values = csim_field::kUnknown;
+    const size_t n = static_cast<size_t>(f->nxt()) * static_cast<size_t>(f->nyt());
+    if (n * sizeof(double) >= kStagedMinBytes) {
+        csim_ctx* c = f->ctx;
+        CSIM_CUDA(cudaSetDevice(c->device));
+        if (int rc = ensure_stage(c, n)) return rc;
+        CSIM_CUDA(cudaMemcpyAsync(c->d_stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CSIM_LAUNCH(c, k_repitch, repitch_grid(f->nxt(), f->nyt()), 256, 0, c->d_stage, f->nxt(), f->at(0, 0),
+                    f->pitch, f->nxt(), f->nyt());
+        return CSIM_OK;
+    }
     return copy2d(f, f->at(0, 0), f->pitch * sizeof(double), host, f->nxt() * sizeof(double), f->nxt(),
                   f->nyt(), cudaMemcpyHostToDevice, false);
 }
@@ -267,6 +308,16 @@ int csim_field_download_interior(const csim_field* f, double* host) {
 int csim_field_download_interior_async(const csim_field* f, double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID,
                  "csim_field_download_interior_async: null argument");
+    const size_t n = static_cast<size_t>(f->nx) * static_cast<size_t>(f->ny);
+    if (n * sizeof(double) >= kStagedMinBytes) {
+        csim_ctx* c = f->ctx;
+        CSIM_CUDA(cudaSetDevice(c->device));
+        if (int rc = ensure_stage(c, n)) return rc;
+        CSIM_LAUNCH(c, k_repitch, repitch_grid(f->nx, f->ny), 256, 0, f->interior(), f->pitch, c->d_stage, f->nx,
+                    f->nx, f->ny);
+        CSIM_CUDA(cudaMemcpyAsync(host, c->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        return CSIM_OK;
+    }
     return copy2d(f, host, f->nx * sizeof(double), f->interior(), f->pitch * sizeof(double), f->nx, f->ny,
                   cudaMemcpyDeviceToHost, false);
 }

@@ -37,6 +37,8 @@ struct csim_ctx {
     size_t pack_doubles = 0;
     double* d_snap = nullptr;  // dense big-endian snapshot staging (csim_field_download_interior_be_async)
     size_t snap_doubles = 0;
+    double* d_stage = nullptr;  // dense staging of large asynchronous host transfers (context.cu)
+    size_t stage_doubles = 0;
     double* d_wide = nullptr;  // wide-halo exchange staging: 8 send + 8 recv regions
     size_t wide_doubles = 0;
     // peer-memory halo push (halo.cu): neighbours' tiles and flag words mapped into this process

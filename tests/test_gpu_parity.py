@@ -65,6 +65,19 @@ def test_field_roundtrip_fill_swap_copy_halo_widths(csim, ctx):
     assert bits_equal(pin, a[2:-2, 2:-2])
     e = csim.Field(ctx, 0, 0, 1, 1.0, 1.0)  # empty interior
     assert e.download().shape == (2, 2)
+    # large asynchronous transfers take the staged path (dense DMA + re-pitch kernel), twice in a row
+    # through the same staging buffer, with odd sizes so that no row of the dense layout is aligned
+    for (ny, nx) in ((700, 1025), (1031, 999)):
+        big = rng.standard_normal((ny + 2, nx + 2))
+        hin = ctx.pinned_empty(big.shape)
+        hin[:] = big
+        hout = ctx.pinned_empty((ny, nx))
+        b = csim.Field(ctx, nx, ny, 1, 1.0, 1.0)
+        b.upload_async(hin)
+        b.download_interior_async(hout)
+        ctx.sync()
+        assert bits_equal(hout, big[1:-1, 1:-1])
+        assert bits_equal(b.download(), big)  # ghost ring included
 
 
 # ---- diffusion_step: test_diffusion.cpp + oracle ----------------------------------------------
