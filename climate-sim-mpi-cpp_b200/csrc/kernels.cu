@@ -472,7 +472,7 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     // chunk height: fill k whole rounds of the resident warp slots of the machine
     const int rows = a.sy1 - a.sy0;
     const int n_edge = a.nstrips >= 2 ? 2 : 1, n_int = a.nstrips - n_edge;
-    const int slots = c->sm_count * (kind == 0 ? kRingBlocksPerSM : kTbBlocksPerSM) * kTbWarpsPerBlock;
+    const int slots = c->sm_count * (kind == 0 ? kRingBlocksPerSM * kRingWarpsPerBlock : kTbBlocksPerSM * kTbWarpsPerBlock);
     const int weight = n_int + n_edge * a.edge_split;
     // Chunk height.  A launch runs as several rounds of resident warps; short chunks keep the last
     // round from idling the machine, tall chunks amortise the 2T rows each chunk re-computes.

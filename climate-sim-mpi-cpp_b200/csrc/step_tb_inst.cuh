@@ -12,6 +12,19 @@ namespace csim {
 
 // kind 1: k_step_tb   (two rows per tick, four rows per level — the default);
 // kind 0: k_step_ring (one row per tick, ring of 2T+3 row slots — CSIM_TB_KERNEL=ring)
+// k_step_ring keeps kRingStages rows per warp in shared memory; ask for the large carve-out once per
+// instantiation so that four CTAs (128 KB) fit on an SM
+template <int T, int MODE, int VXS, int VYS>
+cudaError_t ring_launch(const TbArgs& a, cudaStream_t stream) {
+    const dim3 block(32 * kRingWarpsPerBlock);
+    const dim3 grid((a.n_items + kRingWarpsPerBlock - 1) / kRingWarpsPerBlock);
+    static const cudaError_t prepared = cudaFuncSetAttribute(
+        k_step_ring<T, MODE, VXS, VYS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (prepared != cudaSuccess) return prepared;
+    k_step_ring<T, MODE, VXS, VYS><<<grid, block, kRingSmemBytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <int VXS, int VYS>
 cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStream_t stream) {
     const dim3 block(32 * kTbWarpsPerBlock);
@@ -19,14 +32,9 @@ cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStr
 #define CSIM_TB_CASE(TT, MM)                                                  \
     if (T == TT && mode == MM) {                                              \
         if (kind == 0)                                                        \
-            k_step_ring<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);     \
+            return ring_launch<TT, MM, VXS, VYS>(a, stream);                  \
         else                                                                  \
             k_step_tb<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);       \
-        return cudaGetLastError();                                            \
-    }
-#define CSIM_RING_CASE(TT, MM)                                                \
-    if (T == TT && mode == MM) {                                              \
-        k_step_ring<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);         \
         return cudaGetLastError();                                            \
     }
     if (VXS != 0 && VYS != 0) {
@@ -48,7 +56,6 @@ cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStr
         CSIM_TB_CASE(4, MODE_RECIP)
     }
 #undef CSIM_TB_CASE
-#undef CSIM_RING_CASE
     return cudaErrorInvalidValue;
 }
 
