@@ -384,7 +384,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 64)
-        ref_steps = args.ref_inner * 3
+        ref_steps = args.ref_inner * 20  # ≈ 10 s of CPU work at 8192² on 16 threads
         rate, secs, kind, used = cpu_reference_rate(tile, ref_steps, threads)
         cpu = {"value": rate, "unit": "cell-updates/s", "cores": used, "kind": kind,
                "sample": f"{tile}x{tile}, {ref_steps} time steps of the same workload on {used} emulated ranks "
