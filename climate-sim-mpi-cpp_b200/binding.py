@@ -81,6 +81,10 @@ STEP_FAST_RECIP = 0x1
 STEP_NO_TEMPORAL = 0x2
 
 
+class SweepItem(C.Structure):
+    _fields_ = [("strip", C.c_int), ("x0", C.c_int), ("x1", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
+
+
 class XRegion(C.Structure):
     """csim_xregion"""
     _fields_ = [("x0", C.c_int), ("y0", C.c_int), ("w", C.c_int), ("h", C.c_int), ("peer", C.c_int)]
@@ -143,6 +147,7 @@ def lib():
             "csim_peer_teardown": [vp],
             "csim_wide_exchange_plan": [C.POINTER(_Decomp), C.c_int, C.POINTER(XRegion), C.POINTER(XRegion)],
             "csim_run_steps": [vp, vp, C.POINTER(StepParams), C.POINTER(_Decomp), C.c_int],
+            "csim_sweep_plan": [C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.POINTER(SweepItem), C.c_int, ip],
             "csim_initial_condition_host": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int,
                                             C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                             C.c_double, C.c_double],
@@ -396,6 +401,16 @@ def apply_boundary(f: Field, dec, bc: BCConfig, value: float = 0.0):
 def exchange_halos(f: Field, dec: Decomp2D):
     """include/halo.hpp:7 (the communicator is the one bound to the field's context)"""
     _check(lib().csim_halo_exchange(f._h, C.byref(dec._c)))
+
+
+def sweep_plan(nx: int, ny: int, T: int, nbr=(-1, -1, -1, -1), resident_warps: int = 0, part: int = 0):
+    """csim_sweep_plan (host only): list of (strip, x0, x1, y0, y1) work items of one fused sweep."""
+    nb = (C.c_int * 4)(*nbr)
+    n = C.c_int(0)
+    _check(lib().csim_sweep_plan(nx, ny, T, nb, resident_warps, part, None, 0, C.byref(n)))
+    items = (SweepItem * max(n.value, 1))()
+    _check(lib().csim_sweep_plan(nx, ny, T, nb, resident_warps, part, items, n.value, C.byref(n)))
+    return [(it.strip, it.x0, it.x1, it.y0, it.y1) for it in items[:n.value]]
 
 
 def steps_per_sweep() -> int:

@@ -421,21 +421,26 @@ cudaError_t tb_launch(int vxs, int vys, int kind, int T, int mode, const TbArgs&
     }
 }
 
-int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms) {
-    csim_ctx* c = u->ctx;
-    const int nx = u->nx, ny = u->ny;
-    TbArgs a;
-    a.u = u->interior();
-    a.out = out->interior();
-    a.pitch = u->pitch;
+static int tb_kernel_kind() {
+    // kind 1 = k_step_tb (two rows per tick), the default; CSIM_TB_KERNEL=ring selects k_step_ring
+    // (one row per tick, rotating ring of row slots), which is parity-tested and kept for A/B timing
+    static const int kind = [] {
+        const char* e = std::getenv("CSIM_TB_KERNEL");
+        return (e && std::strcmp(e, "ring") == 0) ? 0 : 1;
+    }();
+    return kind;
+}
+
+// Geometry of one sweep: which cells are advanced / stored / need no boundary fix-up, and how the
+// tile is cut into (strip, chunk) work items.  Pure host arithmetic (csim_sweep_plan exposes it to the
+// CPU tests).  phys: bit s set = side s is a physical boundary; slots: resident warps of the machine.
+// Returns false when the requested part has no work item.
+static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int slots, int kind, int part, TbArgs& a) {
+    a.pitch = pitch;
     a.nx = nx;
     a.ny = ny;
-    a.phys = 0;
-    for (int s = 0; s < 4; ++s)
-        if (p->nbr[s] == CSIM_PROC_NULL) a.phys |= 1 << s;
+    a.phys = phys;
     const bool pl = a.phys & 1, pr = a.phys & 2, pb = a.phys & 4, pt = a.phys & 8;
-    if (launched) *launched = false;
     a.xlo = pl ? 0 : -T;  // ghost lines of a neighbour side are advanced too (their validity shrinks
     a.xhi = pr ? nx : nx + T;  // by one line per level, which is exactly what T lines allow)
     a.ylo = pb ? 0 : -T;
@@ -448,23 +453,11 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.fx1 = pr ? nx - 1 : a.xhi;
     a.fy0 = pb ? 1 : a.ylo;
     a.fy1 = pt ? ny - 1 : a.yhi;
-    a.bcL = p->bc[0];
-    a.bcR = p->bc[1];
-    a.bcB = p->bc[2];
-    a.bcT = p->bc[3];
-    a.value = p->bc_value;
-    a.k = k;
-    a.xmax_load = static_cast<int>(u->pitch) - kLeadX;
-    // kind 1 = k_step_tb (two rows per tick), the default; CSIM_TB_KERNEL=ring selects k_step_ring
-    // (one row per tick, rotating ring of row slots), which is parity-tested and kept for A/B timing
-    static const int kind = [] {
-        const char* e = std::getenv("CSIM_TB_KERNEL");
-        return (e && std::strcmp(e, "ring") == 0) ? 0 : 1;
-    }();
+    a.xmax_load = static_cast<int>(pitch) - kLeadX;
     a.pf_rows = tb_env_int("CSIM_TB_PF", 4);
     a.row_limit = a.pf_rows > 0 ? ny + kLeadY : -(1 << 30);  // <= 0 disables the prefetch branch
     if (a.pf_rows < 0) a.pf_rows = 0;
-    a.pf_off = static_cast<long long>(a.pf_rows) * u->pitch;
+    a.pf_off = static_cast<long long>(a.pf_rows) * pitch;
     a.nstrips = (nx + kTbWout - 1) / kTbWout;
     if (a.nstrips < 1) a.nstrips = 1;
     a.edge_split = tb_env_int("CSIM_TB_EDGE_SPLIT", 2);
@@ -472,7 +465,6 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     // chunk height: fill k whole rounds of the resident warp slots of the machine
     const int rows = a.sy1 - a.sy0;
     const int n_edge = a.nstrips >= 2 ? 2 : 1, n_int = a.nstrips - n_edge;
-    const int slots = c->sm_count * (kind == 0 ? kRingBlocksPerSM * kRingWarpsPerBlock : kTbBlocksPerSM * kTbWarpsPerBlock);
     const int weight = n_int + n_edge * a.edge_split;
     // Chunk height.  A launch runs as several rounds of resident warps; short chunks keep the last
     // round from idling the machine, tall chunks amortise the 2T rows each chunk re-computes.
@@ -505,6 +497,9 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     }
     if (ch > rows) ch = rows;
     if (ch < 1) ch = 1;
+    // a last chunk shorter than T rows would put the ghost-line reads of the bottom T rows into the
+    // chunk before it, which the multi-GPU loop runs while the halos are still travelling
+    for (int tries = 0; tries < 2 * kTbMaxT && ch < rows && rows % ch != 0 && rows % ch < T; ++tries) ++ch;
     a.chunk_h = ch;
     a.nchunks = (rows + ch - 1) / ch;
     const int eh = (ch + a.edge_split - 1) / a.edge_split;
@@ -527,7 +522,8 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
         if (full_rounds >= 1 && n_main >= 1 && n_main * ch < rows) {
             const long long rest = rows - n_main * ch;
             for (int div = 2; div <= 4; ++div) {
-                const int h2 = ch / div < 16 ? 16 : ch / div;
+                int h2 = ch / div < 16 ? 16 : ch / div;
+                for (int tries = 0; tries < 2 * kTbMaxT && rest % h2 != 0 && rest % h2 < T; ++tries) ++h2;
                 const long long n_small = (rest + h2 - 1) / h2;
                 const long long cost = full_rounds * (ch + 2 * T) + ((n_small * n_int + slots - 1) / slots) * (h2 + 2 * T);
                 if (cost < best) {
@@ -543,21 +539,54 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     a.frame_pair = 0;
     int int_chunks = a.nchunks;
     a.n_edge_items = n_edge * nch_edge;
+    // The interior part may run while the halos travel, so none of its items may read a ghost line:
+    // an item reads T rows above and below its chunk and T columns beside its strip's finished
+    // columns.  Chunks 1 … nchunks-2 of strips 1 … nstrips-2 qualify when the first and the last chunk
+    // are at least T rows tall and the last strip is at least T columns wide; otherwise (tiny or
+    // awkward tiles) the sweep is not split and everything runs as the frame.
+    const int first_h = a.n_main >= 1 ? a.chunk_h : a.chunk_h2;
+    const int last_h = a.nchunks > a.n_main
+                           ? rows - a.n_main * a.chunk_h - (a.nchunks - a.n_main - 1) * a.chunk_h2
+                           : rows - (a.nchunks - 1) * a.chunk_h;
+    const int last_w = nx - (a.nstrips - 1) * kTbWout;
+    const bool split_ok = !tb_split_pointless(a.nchunks, n_int) && first_h >= T && last_h >= T && last_w >= T;
     if (part == TB_INTERIOR) {  // interior strips, all chunks but the first and the last
         a.n_edge_items = 0;
         a.int_chunk0 = 1;
-        int_chunks = a.nchunks - 2;
+        int_chunks = split_ok ? a.nchunks - 2 : 0;
     } else if (part == TB_FRAME) {  // both edge strips + first and last chunk of every interior strip
         a.frame_pair = 1;
-        int_chunks = a.nchunks >= 2 ? 2 : a.nchunks;
-        if (tb_split_pointless(a.nchunks, n_int)) {  // the interior part is empty: the frame is everything
+        int_chunks = 2;
+        if (!split_ok) {  // the interior part is empty: the frame is everything
             a.frame_pair = 0;
             int_chunks = a.nchunks;
         }
     }
     if (int_chunks < 0) int_chunks = 0;
     a.n_items = n_int * int_chunks + a.n_edge_items;
-    if (a.n_items <= 0) return CSIM_OK;
+    return a.n_items > 0;
+}
+
+int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
+                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms) {
+    csim_ctx* c = u->ctx;
+    const int kind = tb_kernel_kind();
+    TbArgs a;
+    a.u = u->interior();
+    a.out = out->interior();
+    int phys = 0;
+    for (int s = 0; s < 4; ++s)
+        if (p->nbr[s] == CSIM_PROC_NULL) phys |= 1 << s;
+    if (launched) *launched = false;
+    const int slots =
+        c->sm_count * (kind == 0 ? kRingBlocksPerSM * kRingWarpsPerBlock : kTbBlocksPerSM * kTbWarpsPerBlock);
+    if (!tb_geometry(u->nx, u->ny, u->pitch, T, phys, slots, kind, part, a)) return CSIM_OK;
+    a.bcL = p->bc[0];
+    a.bcR = p->bc[1];
+    a.bcB = p->bc[2];
+    a.bcT = p->bc[3];
+    a.value = p->bc_value;
+    a.k = k;
     if (launched) *launched = true;
     // upwind selectors; a component that is exactly +0.0 may drop its term (tb_update) when the
     // caller established the conditions (zero_terms) and the variant is instantiated
@@ -712,6 +741,41 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
 }
 
 int csim_steps_per_sweep(void) { return tb_max_T(); }
+
+int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps, int part,
+                    csim_sweep_item* items, int capacity, int* count) {
+    CSIM_REQUIRE(nbr != nullptr && count != nullptr && (items != nullptr || capacity == 0), CSIM_ERR_INVALID,
+                 "csim_sweep_plan: null argument");
+    CSIM_REQUIRE(nx >= 1 && ny >= 1 && T >= 1 && T <= kTbMaxT && part >= TB_ALL && part <= TB_FRAME, CSIM_ERR_INVALID,
+                 "csim_sweep_plan: bad size, depth or part");
+    int phys = 0;
+    for (int s = 0; s < 4; ++s)
+        if (nbr[s] == CSIM_PROC_NULL) phys |= 1 << s;
+    const int kind = tb_kernel_kind();
+    const int slots = resident_warps > 0 ? resident_warps : 148 * kTbBlocksPerSM * kTbWarpsPerBlock;
+    const long long pitch = (static_cast<long long>(kLeadX) + nx + kTailX + 15) / 16 * 16;
+    TbArgs a;
+    *count = 0;
+    if (!tb_geometry(nx, ny, pitch, T, phys, slots, kind, part, a)) return CSIM_OK;
+    int n = 0;
+    for (int item = 0; item < a.n_items; ++item) {
+        int strip, ya, yb;
+        if (!tb_item_map(a, item, strip, ya, yb)) continue;
+        if (n < capacity) {
+            csim_sweep_item& it = items[n];
+            it.strip = strip;
+            it.y0 = ya;
+            it.y1 = yb;
+            // finished columns of a strip (step_tb.cuh, tb_store_row): positions 4 … 123 of its 128,
+            // plus the ghost column of a physical side in the first / last strip
+            it.x0 = strip == 0 ? a.sx0 : strip * kTbWout;
+            it.x1 = strip == a.nstrips - 1 ? a.sx1 : (strip + 1) * kTbWout;
+        }
+        ++n;
+    }
+    *count = n;
+    return CSIM_OK;
+}
 
 int csim_minmax(const csim_field* f, double* mn, double* mx) {
     CSIM_REQUIRE(f != nullptr && mn != nullptr && mx != nullptr, CSIM_ERR_INVALID, "csim_minmax: null argument");

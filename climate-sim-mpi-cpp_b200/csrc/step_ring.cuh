@@ -168,29 +168,8 @@ __global__ void __launch_bounds__(32 * kRingWarpsPerBlock, kRingBlocksPerSM) k_s
     const int item = blockIdx.x * kRingWarpsPerBlock + (threadIdx.x >> 5);
     if (item >= a.n_items) return;  // warp-uniform
 
-    // work item → (strip, first row, row count): identical to k_step_tb (the slower edge-strip items
-    // come first so that they never form the tail of the launch)
-    int strip, ya, h;
-    {
-        const int n_edge = a.nstrips >= 2 ? 2 : 1;
-        const int n_int = a.nstrips - n_edge;
-        if (item < a.n_edge_items) {
-            strip = (item % n_edge) ? a.nstrips - 1 : 0;
-            h = (a.chunk_h + a.edge_split - 1) / a.edge_split;
-            ya = a.sy0 + (item / n_edge) * h;
-        } else {
-            const int e = item - a.n_edge_items;
-            strip = 1 + e % n_int;
-            const int ci = e / n_int;
-            const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
-            // the first n_main chunks are chunk_h rows tall, the rest (the tail of the launch) chunk_h2
-            const bool tail = chunk >= a.n_main;
-            h = tail ? a.chunk_h2 : a.chunk_h;
-            ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
-        }
-    }
-    if (ya >= a.sy1) return;
-    const int yb = min(ya + h, a.sy1);
+    int strip, ya, yb;
+    if (!tb_item_map(a, item, strip, ya, yb)) return;
     const int xb = strip * kTbWout - kTbHX;
     TbLane ln;
     ln.x0 = xb + lane * kTbCells;

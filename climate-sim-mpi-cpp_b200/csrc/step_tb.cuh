@@ -68,6 +68,32 @@ struct TbArgs {
     StepK k;
 };
 
+// Work item → (strip, rows [ya, yb)).  Shared by both sweep kernels and by the host-side plan
+// (csim_sweep_plan), which is how the geometry is tested without a GPU.  Interior strips get chunks of
+// chunk_h rows (chunk_h2 in the tail of the launch); the slower edge strips get edge_split times as
+// many chunks of chunk_h/edge_split rows and are enumerated first so that they never form the tail.
+// Returns false for an item without rows.
+__host__ __device__ __forceinline__ bool tb_item_map(const TbArgs& a, int item, int& strip, int& ya, int& yb) {
+    const int n_edge = a.nstrips >= 2 ? 2 : 1;
+    const int n_int = a.nstrips - n_edge;
+    int h;
+    if (item < a.n_edge_items) {
+        strip = (item % n_edge) ? a.nstrips - 1 : 0;
+        h = (a.chunk_h + a.edge_split - 1) / a.edge_split;
+        ya = a.sy0 + (item / n_edge) * h;
+    } else {
+        const int e = item - a.n_edge_items;
+        strip = 1 + e % n_int;
+        const int ci = e / n_int;
+        const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
+        const bool tail = chunk >= a.n_main;
+        h = tail ? a.chunk_h2 : a.chunk_h;
+        ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
+    }
+    yb = ya + h < a.sy1 ? ya + h : a.sy1;
+    return ya < a.sy1;
+}
+
 // One cell update.  VXS / VYS select the upwind side: +1 for v >= 0 (backward difference), -1 for
 // v < 0 (forward difference), 0 for a velocity component that is exactly +0.0, whose whole term is
 // dropped.  Dropping is exact for finite fields without negative zeros: (+0)*d is a signed zero, q + (±0)
@@ -285,30 +311,8 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     const int item = blockIdx.x * kTbWarpsPerBlock + (threadIdx.x >> 5);
     if (item >= a.n_items) return;  // warp-uniform
 
-    // work item → (strip, first row, row count).  Interior strips get chunks of chunk_h rows; the
-    // (slower) edge strips get edge_split times as many chunks of chunk_h/edge_split rows.
-    int strip, ya, h;
-    {
-        // the slower edge-strip items come first so that they never form the tail of the launch
-        const int n_edge = a.nstrips >= 2 ? 2 : 1;
-        const int n_int = a.nstrips - n_edge;
-        if (item < a.n_edge_items) {
-            strip = (item % n_edge) ? a.nstrips - 1 : 0;
-            h = (a.chunk_h + a.edge_split - 1) / a.edge_split;
-            ya = a.sy0 + (item / n_edge) * h;
-        } else {
-            const int e = item - a.n_edge_items;
-            strip = 1 + e % n_int;
-            const int ci = e / n_int;
-            const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
-            // the first n_main chunks are chunk_h rows tall, the rest (the tail of the launch) chunk_h2
-            const bool tail = chunk >= a.n_main;
-            h = tail ? a.chunk_h2 : a.chunk_h;
-            ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
-        }
-    }
-    if (ya >= a.sy1) return;
-    const int yb = min(ya + h, a.sy1);
+    int strip, ya, yb;
+    if (!tb_item_map(a, item, strip, ya, yb)) return;
     const int xb = strip * kTbWout - kTbHX;
     TbLane ln;
     ln.x0 = xb + lane * kTbCells;

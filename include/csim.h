@@ -252,6 +252,20 @@ typedef struct csim_xregion {
  * perpendicular physical side (frozen "periodic" ghosts travel with them); corners are T x T. */
 int csim_wide_exchange_plan(const csim_decomp* dec, int T, csim_xregion send[8], csim_xregion recv[8]);
 
+/* Host-only: the work items one fused sweep of T steps is cut into on a tile of nx x ny cells whose
+ * sides with nbr[s] == CSIM_PROC_NULL are physical, for a machine with `resident_warps` warp slots
+ * (0: 148 SMs x 12).  part: 0 the whole sweep, 1 the items that read no ghost line (overlapped with the
+ * halo exchange), 2 the others (the frame).  Each item is one warp's job: the rows [y0, y1) of the
+ * finished columns [x0, x1) of strip `strip` (interior coordinates; ghost lines of physical sides are
+ * -1 and nx / ny).  Writes at most `capacity` items and returns the total number in *count.  Lets the
+ * geometry be tested without a GPU: the items of part 0 tile the stored region exactly once, and parts
+ * 1 and 2 partition them. */
+typedef struct csim_sweep_item {
+    int strip, x0, x1, y0, y1;
+} csim_sweep_item;
+int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps, int part,
+                    csim_sweep_item* items, int capacity, int* count);
+
 /* ---- the loop ------------------------------------------------------------------------------ */
 
 /* `nsteps` iterations of src/main.cpp:101-109 on this rank: exchange (if the context has a

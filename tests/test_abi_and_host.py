@@ -98,3 +98,53 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not bad.search(text), f
+
+
+# ---- geometry of the fused sweep (csim_sweep_plan, host only) -------------------------------------
+
+def _cover(items, x_lo, x_hi, y_lo, y_hi):
+    """How often each cell of [x_lo,x_hi) x [y_lo,y_hi) is covered by the items' rectangles."""
+    cnt = np.zeros((y_hi - y_lo, x_hi - x_lo), dtype=np.int32)
+    for (_, x0, x1, y0, y1) in items:
+        assert x_lo <= x0 < x1 <= x_hi and y_lo <= y0 < y1 <= y_hi, (x0, x1, y0, y1)
+        cnt[y0 - y_lo:y1 - y_lo, x0 - x_lo:x1 - x_lo] += 1
+    return cnt
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (7, 300), (120, 33), (121, 97), (241, 193), (242, 4099), (513, 257),
+                                   (1000, 1000), (8192, 8192), (8192, 16384), (16384, 8191)])
+def test_sweep_plan_tiles_the_stored_region_exactly_once(csim, nx, ny):
+    """Every stored cell (interior plus the ghost line of each physical side) belongs to exactly one work
+    item — also with the shorter chunks in the tail of the launch, for every blocking depth, for tiles
+    with and without neighbours — and the interior / frame launches of the multi-GPU loop partition
+    the items of the whole sweep."""
+    big = nx * ny >= 4_000_000  # the full-size tiles: default depth and machine only (keeps the suite short)
+    for T in ((3,) if big else (1, 2, 3, 4)):
+        for nbr in ((-1, -1, -1, -1), (3, -1, -1, 5), (-1, 2, 7, -1), (1, 2, 3, 4)):
+            for slots in ((1776,) if big else (0, 64, 1776)):
+                x_lo, x_hi = (-1 if nbr[0] < 0 else 0), (nx + 1 if nbr[1] < 0 else nx)
+                y_lo, y_hi = (-1 if nbr[2] < 0 else 0), (ny + 1 if nbr[3] < 0 else ny)
+                whole = csim.sweep_plan(nx, ny, T, nbr, slots, 0)
+                assert (_cover(whole, x_lo, x_hi, y_lo, y_hi) == 1).all(), (T, nbr, slots)
+                inner = csim.sweep_plan(nx, ny, T, nbr, slots, 1)
+                frame = csim.sweep_plan(nx, ny, T, nbr, slots, 2)
+                assert sorted(inner + frame) == sorted(whole), (T, nbr, slots)
+                # interior items never touch the first/last chunk of a strip nor the edge strips: they
+                # read no ghost line and may run while the halos travel
+                nstrips = max(s for (s, *_r) in whole) + 1
+                for (s, x0, x1, y0, y1) in inner:
+                    assert 0 < s < nstrips - 1 and y0 > y_lo and y1 < y_hi
+                    # its dependency cone (T rows above and below, T columns beside) stays clear of
+                    # the ghost lines of every side that has a neighbour (those lines are in flight)
+                    assert nbr[2] < 0 or y0 - T >= 0, (T, nbr, slots, y0)
+                    assert nbr[3] < 0 or y1 + T <= ny, (T, nbr, slots, y1)
+                    assert nbr[0] < 0 or x0 - T >= 0, (T, nbr, slots, x0)
+                    assert nbr[1] < 0 or x1 + T <= nx, (T, nbr, slots, x1)
+                if nx * ny >= 8192 * 8192 and slots:
+                    assert len(whole) >= slots  # enough items to fill the machine at least once
+
+
+def test_sweep_plan_rejects_bad_arguments(csim):
+    for args in ((0, 5, 3), (5, 0, 3), (5, 5, 0), (5, 5, 5)):
+        with pytest.raises(csim.CsimError):
+            csim.sweep_plan(*args)
