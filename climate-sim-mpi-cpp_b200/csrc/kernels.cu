@@ -2,7 +2,8 @@
 //
 // Arithmetic contract (bit parity with the reference CPU build): every FP64
 // operation is issued through __dadd_rn/__dsub_rn/__dmul_rn/__ddiv_rn, which round to nearest-even
-// and are never contracted into FMA, in exactly the reference's order:
+// and are never contracted into FMA, in exactly the reference's order (the one deliberate FMA of the
+// blocked sweep, e - 2.0*c, rounds the same real number once either way: step_tb.cuh, tb_update):
 //   lap  = ((e - 2.0*c) + w) / (dx*dx) + ((n - 2.0*c) + s) / (dy*dy)      src/diffusion.cpp:12-13
 //   o    = c + (dt*D) * lap                                               src/diffusion.cpp:14
 //   dudx = vx>=0 ? (c - w)/dx : (e - c)/dx                                src/advection.cpp:16-20
@@ -591,8 +592,7 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     // upwind selectors; a component that is exactly +0.0 may drop its term (tb_update) when the
     // caller established the conditions (zero_terms) and the variant is instantiated
     int vxs = k.vx_pos ? 1 : -1, vys = k.vy_pos ? 1 : -1;
-    static const bool force_zero = tb_env_int("CSIM_ZERO_TERMS_FORCE", 0) != 0;  // measurement aid only
-    if ((zero_terms || force_zero) && tb_has_zero_variant(T, mode)) {
+    if (zero_terms && tb_has_zero_variant(T, mode)) {
         if (is_pos_zero(k.vx)) vxs = 0;
         if (is_pos_zero(k.vy)) vys = 0;
     }
