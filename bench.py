@@ -153,6 +153,18 @@ def run_reference(args):
             secs.append(s)
     total_cells = tile * tile * inner * len(secs)
     value = total_cells / sum(secs)
+    # the same objects as the reference's README builds them (no CMAKE_BUILD_TYPE → no optimisation flags):
+    # one short sample, reported beside the -O2 figure, not used for the headline
+    flagless = None
+    try:
+        from oracle import cpu_oracle as co
+        if co.available("ref_O0"):
+            p0 = co.SimParams(nx=tile, ny=tile, steps=1, out_every=10 ** 9, bc=(2, 2, 2, 2), **PHYS)
+            r0 = co.Oracle("ref_O0").run(p0, nranks=threads, want_frames=False, want_final=False)
+            flagless = {"value": tile * tile / r0["seconds"], "unit": "cell-updates/s",
+                        "sample": f"1 time step of the {tile}x{tile} tile, flagless build (-O0) of the reference objects"}
+    except Exception:  # noqa: BLE001
+        flagless = None
     sample = (f"bounded sample: ONE {tile}x{tile} tile (the per-GPU tile of the workload) split over {used} "
               f"emulated ranks (threads), {inner} time steps per bench step, loop time only (main.cpp:89-123 timing region without NetCDF writes); "
               f"reference compute objects, -O2, no MPI launcher (MPI not installed)")
@@ -161,7 +173,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": workload_name(tile, dims_for(args.gpus)), "timesteps_per_step": inner},
-        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": used, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": used, "kind": kind, "sample": sample,
+                         "flagless_build": flagless},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
