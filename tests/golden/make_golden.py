@@ -67,6 +67,31 @@ def cases():
     # decomposition with remainders, 6 ranks {3,2}
     add("ic_6ranks_remainder", SimParams(nx=50, ny=35, D=0.05, vx=0.5, vy=0.3, dt=0.1, steps=12,
                                          out_every=4, bc=(D, N, P, D)), False, nranks=6)
+    # Signed zeros and zero velocity components (second session): flat patches (zero differences), +0.0
+    # cells, -0.0 cells and a -0.0 velocity — the regime in which the GPU path may drop the advection
+    # term of a +0.0 component, and the cases in which it must not.  Wide enough (3 strips) for the
+    # branch-free hot path of the sweep.  A separate generator keeps the cases above unchanged.
+    rz = np.random.default_rng(20261019)
+
+    def add_zero(name, p, negzero):
+        a = rz.standard_normal((p.ny + 2, p.nx + 2)) * 10.0 ** rz.integers(-3, 3, (p.ny + 2, p.nx + 2))
+        for _ in range(10):
+            y, x = rz.integers(0, p.ny), rz.integers(0, p.nx)
+            a[y:y + rz.integers(2, 9), x:x + rz.integers(2, 9)] = rz.choice([0.0, 1.5, -2.25, 1e-300])
+        a[rz.random(a.shape) < 0.03] = 0.0
+        if negzero:
+            a[rz.random(a.shape) < 0.03] = -0.0
+            a[p.ny // 2:p.ny // 2 + 5, p.nx // 2:p.nx // 2 + 6] = -0.0
+        out.append((name, p, a, 1))
+
+    add_zero("zero_vy_flat_patches", SimParams(nx=260, ny=12, D=0.05, vx=0.5, vy=0.0, dt=0.1, steps=7,
+                                               out_every=7, bc=(P, P, P, P)), False)
+    add_zero("zero_vx_negzero_cells", SimParams(nx=260, ny=12, D=0.05, vx=0.0, vy=-0.3, dt=0.1, steps=7,
+                                                out_every=7, bc=(D, N, P, N)), True)
+    add_zero("zero_both_flat_patches", SimParams(nx=260, ny=12, D=0.05, vx=0.0, vy=0.0, dt=0.1, steps=7,
+                                                 out_every=7, bc=(N, D, N, D)), False)
+    add_zero("negzero_velocity", SimParams(nx=260, ny=12, D=0.05, vx=0.5, vy=-0.0, dt=0.1, steps=7,
+                                           out_every=7, bc=(P, P, P, P)), False)
     return out
 
 
