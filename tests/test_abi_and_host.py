@@ -148,3 +148,27 @@ def test_sweep_plan_rejects_bad_arguments(csim):
     for args in ((0, 5, 3), (5, 0, 3), (5, 5, 0), (5, 5, 5)):
         with pytest.raises(csim.CsimError):
             csim.sweep_plan(*args)
+
+
+def test_sweep_plan_random_geometries(csim):
+    """The same three properties (exact tiling, interior + frame = whole, interior items clear of in-flight
+    ghost lines) over a few hundred random tile sizes, depths, neighbour sets and machine sizes."""
+    rng = np.random.default_rng(314159)
+    for _ in range(300):
+        nx = int(rng.choice([rng.integers(1, 40), rng.integers(100, 400), rng.integers(400, 2600)]))
+        ny = int(rng.choice([rng.integers(1, 40), rng.integers(30, 300), rng.integers(300, 2600)]))
+        T = int(rng.integers(1, 5))
+        nbr = tuple(int(v) for v in rng.choice([-1, 1], size=4))
+        slots = int(rng.choice([0, 8, 96, 512, 1776, 2368]))
+        x_lo, x_hi = (-1 if nbr[0] < 0 else 0), (nx + 1 if nbr[1] < 0 else nx)
+        y_lo, y_hi = (-1 if nbr[2] < 0 else 0), (ny + 1 if nbr[3] < 0 else ny)
+        whole = csim.sweep_plan(nx, ny, T, nbr, slots, 0)
+        assert (_cover(whole, x_lo, x_hi, y_lo, y_hi) == 1).all(), (nx, ny, T, nbr, slots)
+        inner = csim.sweep_plan(nx, ny, T, nbr, slots, 1)
+        frame = csim.sweep_plan(nx, ny, T, nbr, slots, 2)
+        assert sorted(inner + frame) == sorted(whole), (nx, ny, T, nbr, slots)
+        for (s, x0, x1, y0, y1) in inner:
+            assert nbr[2] < 0 or y0 - T >= 0, (nx, ny, T, nbr, slots, y0)
+            assert nbr[3] < 0 or y1 + T <= ny, (nx, ny, T, nbr, slots, y1)
+            assert nbr[0] < 0 or x0 - T >= 0, (nx, ny, T, nbr, slots, x0)
+            assert nbr[1] < 0 or x1 + T <= nx, (nx, ny, T, nbr, slots, x1)
