@@ -18,7 +18,8 @@ from enum import IntEnum
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsim_b200.so")
+# CSIM_LIB_PATH: A/B timing of two builds of the same library (tools/); never a different implementation
+LIB_PATH = os.environ.get("CSIM_LIB_PATH") or os.path.join(_HERE, "libcsim_b200.so")
 
 PROC_NULL = -1  # MPI_PROC_NULL
 UNIQUE_ID_BYTES = 128
@@ -143,8 +144,6 @@ def lib():
             "csim_comm_destroy": [vp],
             "csim_comm_allreduce_max": [vp, dp, C.c_int],
             "csim_halo_exchange": [vp, C.POINTER(_Decomp)],
-            "csim_peer_setup": [vp, vp, C.POINTER(_Decomp)],
-            "csim_peer_teardown": [vp],
             "csim_wide_exchange_plan": [C.POINTER(_Decomp), C.c_int, C.POINTER(XRegion), C.POINTER(XRegion)],
             "csim_run_steps": [vp, vp, C.POINTER(StepParams), C.POINTER(_Decomp), C.c_int],
             "csim_sweep_plan": [C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.POINTER(SweepItem), C.c_int, ip],
@@ -423,16 +422,6 @@ def wide_exchange_plan(dec: Decomp2D, T: int):
     snd, rcv = (XRegion * 8)(), (XRegion * 8)()
     _check(lib().csim_wide_exchange_plan(C.byref(dec._c), T, snd, rcv))
     return list(snd), list(rcv)
-
-
-def peer_setup(u: Field, tmp: Field, dec: Decomp2D):
-    """Collective: map the neighbours' tiles (CUDA IPC / peer access) so run_steps pushes halos
-    directly into their ghost lines instead of going through NCCL."""
-    _check(lib().csim_peer_setup(u._h, tmp._h, C.byref(dec._c)))
-
-
-def peer_teardown(ctx: Context):
-    _check(lib().csim_peer_teardown(ctx._h))
 
 
 def safe_dt(dx, dy, vx, vy, D) -> float:

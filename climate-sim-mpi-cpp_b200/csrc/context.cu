@@ -111,7 +111,8 @@ int csim_ctx_create(int device, csim_ctx** out) {
 int csim_ctx_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
-    csim_peer_teardown(c);
+    cudaDeviceSynchronize();
+    run_state_destroy(c);  // graphs hold NCCL kernels: they go before the communicator
     if (c->comm) csim_comm_destroy(c);
     // tiles that outlive their context (garbage-collection order in a host language) are orphaned:
     // their device memory goes now, csim_field_destroy later only frees the handle
@@ -148,8 +149,6 @@ int csim_sync(csim_ctx* c) {
     CSIM_CUDA(cudaSetDevice(c->device));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
-    if (c->h_err && *c->h_err)
-        return fail(CSIM_ERR_TIMEOUT, "csim_sync: a neighbour's halo did not arrive within the bounded wait");
     return CSIM_OK;
 }
 
@@ -204,10 +203,6 @@ int csim_field_destroy(csim_field* f) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->stream_x);
-    // a tile that is mapped by the neighbours takes the peer links down with it: a later tile may
-    // get the same address, and pushing through stale mappings would corrupt the neighbours
-    if (f->ctx->peer_ready && (f->base == f->ctx->peer_tile[0] || f->base == f->ctx->peer_tile[1]))
-        csim_peer_teardown(f->ctx);
     if (f->base) cudaFree(f->base);
     delete f;
     return CSIM_OK;

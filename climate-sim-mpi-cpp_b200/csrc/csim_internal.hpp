@@ -41,22 +41,7 @@ struct csim_ctx {
     size_t stage_doubles = 0;
     double* d_wide = nullptr;  // wide-halo exchange staging: 8 send + 8 recv regions
     size_t wide_doubles = 0;
-    // peer-memory halo push (halo.cu): neighbours' tiles and flag words mapped into this process
-    struct PeerLink {
-        int rank = -1;
-        double* tile[2] = {nullptr, nullptr};  // the neighbour's two tile allocations (its u, tmp at setup)
-        long long pitch = 0;
-        int nx = 0, ny = 0;
-        unsigned* flags = nullptr;             // the neighbour's flag words
-        bool ipc = false;                      // mapped with cudaIpcOpenMemHandle (else same-process pointers)
-    };
-    PeerLink peer[8];
-    bool peer_ready = false;
-    double* peer_tile[2] = {nullptr, nullptr};  // this rank's two allocations, in the order given at setup
-    unsigned* d_flags = nullptr;                // [0..7] written by the neighbours, [8] push ticket
-    unsigned* h_err = nullptr;                  // pinned, mapped: set by the wait kernel on timeout
-    unsigned* d_err = nullptr;
-    unsigned push_seq = 0;
+    void* run_state = nullptr;        // halo.cu: captured block loops (CUDA graphs) and the halo timeline
     cudaStream_t stream_x = nullptr;  // exchange + frame sweep, overlapped with the interior sweep
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_go = nullptr;
     int sm_count = 148;
@@ -90,6 +75,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // 1/x is exact and x*(1/x)==1 iff x is a (normal) power of two
 bool is_pow2(double x);
 
+void run_state_destroy(csim_ctx* c);  // halo.cu
 struct StepK;
 enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2 };
 int tb_max_T();

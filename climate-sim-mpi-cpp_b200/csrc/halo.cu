@@ -14,8 +14,6 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
-#include <unistd.h>
-
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -134,8 +132,31 @@ __global__ void __launch_bounds__(256) k_unpack_regions(double* __restrict__ u, 
     }
 }
 
-// Fill T ghost lines of `f` on every side that has a neighbour, on `stream`.
-static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream) {
+// Staging of the wide exchange: 8 send + 8 receive regions of up to T lines.  Sized before the block
+// loop (never inside a stream capture).
+static int ensure_wide(csim_ctx* c, const csim_field* f, const csim_decomp* dec, int T) {
+    csim_decomp d = *dec;
+    d.nx_local = f->nx;
+    d.ny_local = f->ny;
+    csim_xregion ps[8], pr8[8];
+    if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
+    size_t total = 0;
+    for (int q = 0; q < 8; ++q) total += static_cast<size_t>(ps[q].w) * ps[q].h;
+    if (c->wide_doubles >= 2 * total) return CSIM_OK;
+    if (c->d_wide) {
+        CSIM_CUDA(cudaDeviceSynchronize());
+        CSIM_CUDA(cudaFree(c->d_wide));
+        c->d_wide = nullptr;
+        c->wide_doubles = 0;
+    }
+    CSIM_CUDA(cudaMalloc(&c->d_wide, 2 * total * sizeof(double)));
+    c->wide_doubles = 2 * total;
+    return CSIM_OK;
+}
+
+// Fill T ghost lines of `f` on every side that has a neighbour, on `stream`.  *bytes_sent (optional)
+// receives what this rank puts on the wire.
+static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream, size_t* bytes_sent) {
     csim_ctx* c = f->ctx;
     csim_decomp d = *dec;  // the plan is a function of the decomposition; the tile fixes the local size
     d.nx_local = f->nx;
@@ -143,23 +164,18 @@ static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     csim_xregion ps[8], pr8[8];
     if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
     XTable snd, rcv;
-    long long off = 0;
+    long long off = 0, wire = 0;
     for (int q = 0; q < 8; ++q) {
         snd.r[q] = XRegion{ps[q].x0, ps[q].y0, ps[q].w, ps[q].h, off, ps[q].peer};
         rcv.r[q] = XRegion{pr8[q].x0, pr8[q].y0, pr8[q].w, pr8[q].h, 0, pr8[q].peer};
         off += static_cast<long long>(ps[q].w) * ps[q].h;
+        if (ps[q].peer >= 0) wire += static_cast<long long>(ps[q].w) * ps[q].h;
     }
     const long long send_total = off;
     for (int q = 0; q < 8; ++q) rcv.r[q].off = send_total + snd.r[q].off;
-    if (c->wide_doubles < static_cast<size_t>(2 * send_total)) {
-        if (c->d_wide) {
-            CSIM_CUDA(cudaDeviceSynchronize());
-            CSIM_CUDA(cudaFree(c->d_wide));
-            c->d_wide = nullptr;
-        }
-        CSIM_CUDA(cudaMalloc(&c->d_wide, static_cast<size_t>(2 * send_total) * sizeof(double)));
-        c->wide_doubles = static_cast<size_t>(2 * send_total);
-    }
+    CSIM_REQUIRE(c->wide_doubles >= static_cast<size_t>(2 * send_total), CSIM_ERR_INVALID,
+                 "wide_exchange: staging buffer not sized (ensure_wide)");
+    if (bytes_sent) *bytes_sent = static_cast<size_t>(wire) * sizeof(double);
     double* buf = c->d_wide;
     const dim3 grid(32, 8);
     k_pack_regions<<<grid, 256, 0, stream>>>(f->interior(), f->pitch, snd, buf);
@@ -181,129 +197,176 @@ static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     return CSIM_OK;
 }
 
-// ---- peer-memory exchange: store the bands straight into the neighbours' ghost lines ---------------
-struct PushRegion {
-    int x0, y0, w, h;     // source region in this rank's tile (interior coordinates)
-    double* dst;          // neighbour's cell that receives the region's first cell (mapped pointer)
-    long long dst_pitch;  // neighbour's row pitch
-    unsigned* flag;       // neighbour's flag word for this direction, nullptr: no neighbour
+// ---- the block loop of csim_run_steps, its CUDA-graph replay and its timeline -----------------------
+
+// Everything a captured block loop depends on; two calls with equal keys enqueue identical work.
+struct RunKey {
+    const double* u;
+    const double* tmp;
+    int nsteps, maxT, mode, zero_terms;
+    csim_step_params p;
+    csim_decomp d;
 };
-struct PushTable {
-    PushRegion r[8];
+static bool same_key(const RunKey& a, const RunKey& b) { return std::memcmp(&a, &b, sizeof(RunKey)) == 0; }
+
+struct RunGraph {
+    RunKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;  // kernels one replay launches
+    int swaps = 0;          // buffer swaps one replay stands for
+    uint64_t last_use = 0;
 };
 
-// Copy all regions, then (last CTA only, after a system-scope fence) publish `seq` in every
-// neighbour's flag word.  Few small CTAs on purpose: the kernel has to find SM slots while the
-// interior sweep fills the machine.
-__global__ void __launch_bounds__(128) k_push_regions(const double* __restrict__ u, long long pitch, PushTable t,
-                                                      unsigned seq, unsigned* __restrict__ ticket) {
-    for (int q = 0; q < 8; ++q) {
-        const PushRegion g = t.r[q];
-        if (!g.flag) continue;
-        const int n = g.w * g.h;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-            const int yy = e / g.w, xx = e - yy * g.w;
-            g.dst[static_cast<long long>(yy) * g.dst_pitch + xx] =
-                u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx];
+// Timeline of one profiled call (csim_halo_profile): per block, timestamps around the exchange and the
+// frame sweep on the exchange stream and around the interior sweep on the main stream.
+struct RunProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // base, then 6 per block: x0 x1 f1 i0 i1 (f0 == x1) + spare
+    size_t used = 0;
+    int blocks = 0;
+    size_t bytes_per_exchange = 0;
+    cudaEvent_t next(csim_ctx* c) {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaSetDevice(c->device);
+            cudaEventCreate(&e);
+            ev.push_back(e);
         }
+        return ev[used++];
     }
-    __threadfence_system();  // this thread's peer stores are visible system-wide before the ticket
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last && threadIdx.x < 8) {
-        if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next push (stream order protects it)
-        unsigned* f = t.r[threadIdx.x].flag;
-        if (f) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned*>(f) = seq;
-        }
-    }
+};
+
+struct RunState {
+    std::vector<RunGraph> graphs;
+    uint64_t tick = 0;
+    bool comm_warm = false;  // one eager pass has set up NCCL's connections to every neighbour
+    RunProfile prof;
+    csim_halo_stats last{};
+};
+
+static RunState* run_state(csim_ctx* c) {
+    if (!c->run_state) c->run_state = new RunState();
+    return static_cast<RunState*>(c->run_state);
 }
 
-// Gate of the frame sweep: wait until every neighbour in `mask` has published >= seq.  Bounded: after
-// `timeout_ns` the kernel records the failure and returns, so a lost neighbour ends in an error code.
-__global__ void k_wait_flags(const unsigned* flags, unsigned mask, unsigned seq, unsigned long long timeout_ns,
-                             unsigned* err) {
-    const int k = threadIdx.x;
-    if (k >= 8 || !((mask >> k) & 1)) return;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-    const volatile unsigned* f = flags + k;
-    // seq wraps after 2^32 exchanges; compare as a signed distance
-    while (static_cast<int>(*f - seq) < 0) {
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > timeout_ns) {
-            atomicExch(err, 1u + static_cast<unsigned>(k));
-            return;
+void run_state_destroy(csim_ctx* c) {
+    RunState* rs = static_cast<RunState*>(c->run_state);
+    if (!rs) return;
+    for (RunGraph& g : rs->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (cudaEvent_t e : rs->prof.ev) cudaEventDestroy(e);
+    delete rs;
+    c->run_state = nullptr;
+}
+
+// Software pipeline over blocks of T steps, two streams:
+//   exchange stream (high priority): go(n) → frame(n) → exchange(n+1)
+//   main stream                    : wait go(n) → interior(n)
+// frame(n) = the work items that read ghost lines (edge strips, first/last chunk of every strip);
+// interior(n) = all the others.  The bands exchange(n+1) packs are all produced by frame(n), so
+// the next block's halos travel while interior(n) runs and are in place when block n+1 starts.
+//   frame(n)    needs exchange(n) (same stream) and interior(n-1) (event ev_fork)
+//   interior(n) needs frame(n-1) and interior(n-1); it is released by the event go(n), recorded
+//               on the exchange stream right before frame(n), so that both kernels become
+//               eligible together and the high-priority frame blocks are placed first.  Released
+//               by stream order alone, the interior blocks fill every SM a few microseconds
+//               before the frame's event arrives and the frame waits a whole round for slots:
+//               measured chain frame-wait 88 + frame 88 + exchange 132 us = 308 us per block
+//               against 285 us of work (profiles/r01_multigpu_phases.md).
+// Swaps u and tmp once per block (host bookkeeping); *swaps returns how often.
+static int enqueue_blocks(csim_field* u, csim_field* tmp, const csim_step_params* p, const csim_decomp* dec,
+                          const StepK& k, int mode, int maxT, int nsteps, bool zero_terms, int values_after,
+                          RunProfile* prof, int* swaps) {
+    csim_ctx* c = u->ctx;
+    int left = nsteps;
+    int T = left < maxT ? left : maxT;
+    *swaps = 0;
+    auto stamp = [&](cudaStream_t st) -> int {
+        if (!prof) return CSIM_OK;
+        CSIM_CUDA(cudaEventRecord(prof->next(c), st));
+        return CSIM_OK;
+    };
+    CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // everything queued so far = "interior(-1)"
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+    if (int rc = stamp(c->stream_x)) return rc;  // x0(0)
+    size_t wire = 0;
+    if (int rc = wide_exchange(u, dec, T, c->stream_x, &wire)) return rc;  // exchange(0): the only one not hidden
+    if (prof) prof->bytes_per_exchange = wire;
+    bool first = true;
+    while (left > 0) {
+        bool launched = false;
+        if (!first) CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));  // interior(n-1) done
+        if (int rc = stamp(c->stream_x)) return rc;                              // x1(n) = f0(n)
+        CSIM_CUDA(cudaEventRecord(c->ev_go, c->stream_x));                       // go(n)
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched, zero_terms)) return rc;
+        CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));                     // frame(n) done
+        if (int rc = stamp(c->stream_x)) return rc;                              // f1(n)
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_go, 0));
+        if (int rc = stamp(c->stream)) return rc;                                // i0(n)
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched, zero_terms)) return rc;
+        if (int rc = stamp(c->stream)) return rc;                                // i1(n)
+        CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));                       // interior(n) done
+        tmp->values = values_after;
+        csim_field_swap(u, tmp);
+        ++*swaps;
+        if (prof) ++prof->blocks;
+        left -= T;
+        first = false;
+        if (left > 0) {
+            T = left < maxT ? left : maxT;
+            if (int rc = stamp(c->stream_x)) return rc;                          // x0(n+1)
+            if (int rc = wide_exchange(u, dec, T, c->stream_x, nullptr)) return rc;  // exchange(n+1): reads frame(n)'s cells
         }
-        __nanosleep(200);
     }
-    __threadfence_system();
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the main stream orders everything again
+    return CSIM_OK;
 }
 
-static bool peer_path_enabled(const csim_ctx* c, const csim_field* u, const csim_field* tmp) {
-    if (!c->peer_ready) return false;
-    static const bool force_nccl = [] {
-        const char* e = std::getenv("CSIM_HALO");
-        return e && std::strcmp(e, "nccl") == 0;
-    }();
-    if (force_nccl) return false;
-    return (u->base == c->peer_tile[0] && tmp->base == c->peer_tile[1]) ||
-           (u->base == c->peer_tile[1] && tmp->base == c->peer_tile[0]);
-}
-
-// Peer version of wide_exchange: push this rank's bands of tile `f` into the neighbours' copy of
-// the same tile, then gate `stream` on the neighbours' pushes into ours.
-static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream) {
-    csim_ctx* c = f->ctx;
-    csim_decomp d = *dec;
-    d.nx_local = f->nx;
-    d.ny_local = f->ny;
-    csim_xregion ps[8], pr8[8];
-    if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
-    const int slot = f->base == c->peer_tile[0] ? 0 : 1;
-    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL;
-    PushTable t;
-    unsigned mask = 0;
-    int q = 0;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (dx == 0 && dy == 0) continue;
-            PushRegion& g = t.r[q];
-            g.x0 = ps[q].x0;
-            g.y0 = ps[q].y0;
-            g.w = ps[q].w;
-            g.h = ps[q].h;
-            g.dst = nullptr;
-            g.dst_pitch = 0;
-            g.flag = nullptr;
-            const csim_ctx::PeerLink& L = c->peer[q];
-            if (ps[q].peer >= 0) {
-                CSIM_REQUIRE(L.rank == ps[q].peer && L.tile[slot] != nullptr, CSIM_ERR_COMM,
-                             "peer_exchange: neighbour not mapped (csim_peer_setup with other tiles?)");
-                // my region lands in the neighbour's ghost area on ITS side (-dx,-dy): its own
-                // receive rule with its own tile size (bands keep their along-side origin: the
-                // neighbour shares that physical side with me)
-                const int rx = dx > 0 ? -T : (dx < 0 ? L.nx : (pl ? -1 : 0));
-                const int ry = dy > 0 ? -T : (dy < 0 ? L.ny : (pb ? -1 : 0));
-                double* interior = L.tile[slot] + static_cast<long long>(kLeadY) * L.pitch + kLeadX;
-                g.dst = interior + static_cast<long long>(ry) * L.pitch + rx;
-                g.dst_pitch = L.pitch;
-                g.flag = L.flags + (7 - q);  // the slot of direction (-dx,-dy) in the neighbour's array
-                mask |= 1u << q;
-            }
-            ++q;
+// Turn the recorded timeline into csim_halo_stats (host-synchronous; profiled calls only).
+static int finish_profile(csim_ctx* c, RunState* rs) {
+    RunProfile& pr = rs->prof;
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    csim_halo_stats st{};
+    st.blocks = pr.blocks;
+    st.bytes_per_exchange = pr.bytes_per_exchange;
+    // event layout: base, x0(0), then per block n: x1(n) f1(n) i0(n) i1(n) [x0(n+1) unless last]
+    std::vector<double> t(pr.used, 0.0);
+    for (size_t i = 1; i < pr.used; ++i) {
+        float ms = 0.f;
+        CSIM_CUDA(cudaEventElapsedTime(&ms, pr.ev[0], pr.ev[i]));
+        t[i] = ms;
+    }
+    double ex = 0.0, hidden = 0.0, frame = 0.0, interior = 0.0;
+    int n_hidden = 0;
+    size_t i = 1;  // t[0] is the time base
+    double x0 = t[i++];
+    double prev_i0 = 0.0, prev_i1 = 0.0;
+    for (int n = 0; n < pr.blocks && i + 3 < pr.used; ++n) {
+        const double x1 = t[i], f1 = t[i + 1], i0 = t[i + 2], i1 = t[i + 3];
+        i += 4;
+        const double dur = x1 - x0;
+        if (n == 0) {
+            st.first_exchange_us = 1e3 * dur;
+        } else {  // exchange(n) ran beside interior(n-1): how much of it lies inside that interval
+            ex += dur;
+            const double lo = x0 > prev_i0 ? x0 : prev_i0, hi = x1 < prev_i1 ? x1 : prev_i1;
+            if (hi > lo) hidden += hi - lo;
+            ++n_hidden;
         }
-    const unsigned seq = ++c->push_seq;
-    k_push_regions<<<8, 128, 0, stream>>>(f->interior(), f->pitch, t, seq, c->d_flags + 8);
-    ++c->launches;
-    CSIM_CUDA(cudaGetLastError());
-    k_wait_flags<<<1, 32, 0, stream>>>(c->d_flags, mask, seq, 5000000000ull, c->d_err);
-    ++c->launches;
-    CSIM_CUDA(cudaGetLastError());
+        frame += f1 - x1;
+        interior += i1 - i0;
+        prev_i0 = i0;
+        prev_i1 = i1;
+        if (n + 1 < pr.blocks && i < pr.used) x0 = t[i++];
+    }
+    st.exchange_us = n_hidden ? 1e3 * ex / n_hidden : st.first_exchange_us;
+    st.overlap_fraction = ex > 0.0 ? hidden / ex : 0.0;
+    st.frame_us = pr.blocks ? 1e3 * frame / pr.blocks : 0.0;
+    st.interior_us = pr.blocks ? 1e3 * interior / pr.blocks : 0.0;
+    st.total_ms = pr.used ? t[pr.used - 1] : 0.0;
+    rs->last = st;
+    pr.on = false;
     return CSIM_OK;
 }
 
@@ -370,131 +433,6 @@ int csim_comm_allreduce_max(csim_ctx* c, double* inout, int n) {
     CSIM_CUDA(cudaMemcpyAsync(c->h_scratch, c->d_scratch, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < n; ++k) inout[k] = c->h_scratch[k];
-    return CSIM_OK;
-}
-
-// Bootstrap record every rank contributes to the all-gather in csim_peer_setup.
-struct PeerInfo {
-    cudaIpcMemHandle_t tile[2];
-    cudaIpcMemHandle_t flags;
-    unsigned long long raw_tile[2], raw_flags;  // same-process pointers
-    long long pid;
-    long long pitch;
-    int nx, ny, device, pad;
-};
-
-int csim_peer_teardown(csim_ctx* c) {
-    CSIM_REQUIRE(c != nullptr, CSIM_ERR_INVALID, "csim_peer_teardown: ctx is null");
-    if (!c->peer_ready && !c->d_flags) return CSIM_OK;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->stream_x);
-    for (auto& L : c->peer) {
-        if (L.ipc) {
-            for (double*& t : L.tile)
-                if (t) cudaIpcCloseMemHandle(t);
-            if (L.flags) cudaIpcCloseMemHandle(L.flags);
-        }
-        L = csim_ctx::PeerLink();
-    }
-    c->peer_ready = false;
-    if (c->d_flags) cudaFree(c->d_flags);
-    c->d_flags = nullptr;
-    if (c->h_err) cudaFreeHost(c->h_err);
-    c->h_err = nullptr;
-    c->d_err = nullptr;
-    return CSIM_OK;
-}
-
-int csim_peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec) {
-    CSIM_REQUIRE(u != nullptr && tmp != nullptr && dec != nullptr, CSIM_ERR_INVALID, "csim_peer_setup: null argument");
-    csim_ctx* c = u->ctx;
-    CSIM_REQUIRE(c == tmp->ctx && u->pitch == tmp->pitch && u->nx == tmp->nx && u->ny == tmp->ny, CSIM_ERR_INVALID,
-                 "csim_peer_setup: tiles differ in geometry");
-    CSIM_REQUIRE(c->comm != nullptr, CSIM_ERR_COMM, "csim_peer_setup: needs csim_comm_init first");
-    CSIM_CUDA(cudaSetDevice(c->device));
-    if (int rc = csim_peer_teardown(c)) return rc;
-    const int size = c->comm_size, me = c->comm_rank;
-    CSIM_CUDA(cudaMalloc(&c->d_flags, 16 * sizeof(unsigned)));
-    CSIM_CUDA(cudaMemset(c->d_flags, 0, 16 * sizeof(unsigned)));
-    CSIM_CUDA(cudaHostAlloc(&c->h_err, sizeof(unsigned), cudaHostAllocMapped));
-    *c->h_err = 0;
-    CSIM_CUDA(cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
-    c->push_seq = 0;
-    c->peer_tile[0] = u->base;
-    c->peer_tile[1] = tmp->base;
-
-    PeerInfo mine;
-    std::memset(&mine, 0, sizeof mine);
-    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[0], u->base));
-    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[1], tmp->base));
-    CSIM_CUDA(cudaIpcGetMemHandle(&mine.flags, c->d_flags));
-    mine.raw_tile[0] = reinterpret_cast<unsigned long long>(u->base);
-    mine.raw_tile[1] = reinterpret_cast<unsigned long long>(tmp->base);
-    mine.raw_flags = reinterpret_cast<unsigned long long>(c->d_flags);
-    mine.pid = static_cast<long long>(getpid());
-    mine.pitch = u->pitch;
-    mine.nx = u->nx;
-    mine.ny = u->ny;
-    mine.device = c->device;
-
-    // all-gather of the records over the communicator that is already there
-    static_assert(sizeof(PeerInfo) % 8 == 0, "PeerInfo must be a whole number of doubles");
-    const size_t words = sizeof(PeerInfo) / 8;
-    double* d_all = nullptr;
-    CSIM_CUDA(cudaMalloc(&d_all, sizeof(PeerInfo) * static_cast<size_t>(size + 1)));
-    CSIM_CUDA(cudaMemcpyAsync(d_all + words * size, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
-    CSIM_NCCL(g_nccl.AllGather(d_all + words * size, d_all, words, ncclDouble, static_cast<ncclComm_t>(c->comm),
-                               c->stream));
-    std::vector<PeerInfo> all(static_cast<size_t>(size));
-    CSIM_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * static_cast<size_t>(size), cudaMemcpyDeviceToHost,
-                              c->stream));
-    CSIM_CUDA(cudaStreamSynchronize(c->stream));
-    CSIM_CUDA(cudaFree(d_all));
-
-    const int cx = dec->coords[0], cy = dec->coords[1];
-    int q = 0;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (dx == 0 && dy == 0) continue;
-            csim_ctx::PeerLink& L = c->peer[q++];
-            const int x = cx + dx, y = cy + dy;
-            if (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) continue;
-            const int r = x * dec->dims[1] + y;
-            CSIM_REQUIRE(r != me && r < size, CSIM_ERR_INVALID, "csim_peer_setup: bad neighbour rank");
-            const PeerInfo& o = all[static_cast<size_t>(r)];
-            L.rank = r;
-            L.pitch = o.pitch;
-            L.nx = o.nx;
-            L.ny = o.ny;
-            if (o.pid == mine.pid) {  // ranks are threads of one process: plain peer access
-                if (o.device != c->device) {
-                    cudaError_t e = cudaDeviceEnablePeerAccess(o.device, 0);
-                    if (e == cudaErrorPeerAccessAlreadyEnabled)
-                        cudaGetLastError();
-                    else if (e != cudaSuccess)
-                        return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
-                }
-                L.tile[0] = reinterpret_cast<double*>(o.raw_tile[0]);
-                L.tile[1] = reinterpret_cast<double*>(o.raw_tile[1]);
-                L.flags = reinterpret_cast<unsigned*>(o.raw_flags);
-                L.ipc = false;
-            } else {
-                void* p0 = nullptr;
-                void* p1 = nullptr;
-                void* pf = nullptr;
-                CSIM_CUDA(cudaIpcOpenMemHandle(&p0, o.tile[0], cudaIpcMemLazyEnablePeerAccess));
-                CSIM_CUDA(cudaIpcOpenMemHandle(&p1, o.tile[1], cudaIpcMemLazyEnablePeerAccess));
-                CSIM_CUDA(cudaIpcOpenMemHandle(&pf, o.flags, cudaIpcMemLazyEnablePeerAccess));
-                L.tile[0] = static_cast<double*>(p0);
-                L.tile[1] = static_cast<double*>(p1);
-                L.flags = static_cast<unsigned*>(pf);
-                L.ipc = true;
-            }
-        }
-    // nobody pushes before everyone has mapped everyone (and zeroed its flags)
-    if (int rc = csim_comm_allreduce_max(c, nullptr, 0)) return rc;
-    c->peer_ready = true;
     return CSIM_OK;
 }
 
@@ -588,57 +526,100 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
         }
         return CSIM_OK;
     }
-    // Software pipeline over blocks of T steps, two streams:
-    //   exchange stream (high priority): go(n) → frame(n) → exchange(n+1)
-    //   main stream                    : wait go(n) → interior(n)
-    // frame(n) = the work items that read ghost lines (edge strips, first/last chunk of every strip);
-    // interior(n) = all the others.  The bands exchange(n+1) packs are all produced by frame(n), so
-    // the next block's halos travel while interior(n) runs and are in place when block n+1 starts.
-    //   frame(n)    needs exchange(n) (same stream) and interior(n-1) (event ev_fork)
-    //   interior(n) needs frame(n-1) and interior(n-1); it is released by the event go(n), recorded
-    //               on the exchange stream right before frame(n), so that both kernels become
-    //               eligible together and the high-priority frame blocks are placed first.  Released
-    //               by stream order alone, the interior blocks fill every SM a few microseconds
-    //               before the frame's event arrives and the frame waits a whole round for slots:
-    //               measured chain frame-wait 88 + frame 88 + exchange 132 us = 308 us per block
-    //               against 285 us of work (profiles/r01_multigpu_phases.md).
     // one decision for the whole call, taken per rank (see resolve_zero_terms)
     bool zero_terms = false;
     if (nsteps >= maxT)
         if (int rc = resolve_zero_terms(u, p, k, mode, maxT, &zero_terms)) return rc;
     const int values_after = zero_terms ? csim_field::kClean
                                         : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
-    const bool p2p = peer_path_enabled(c, u, tmp);
-    if (p2p && *c->h_err)
-        return fail(CSIM_ERR_TIMEOUT, "csim_run_steps: a neighbour's halo did not arrive within the bounded wait");
-    auto exchange = [&](csim_field* f, int lines) {
-        return p2p ? peer_exchange(f, dec, lines, c->stream_x) : wide_exchange(f, dec, lines, c->stream_x);
-    };
-    int left = nsteps;
-    int T = left < maxT ? left : maxT;
-    CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // everything queued so far = "interior(-1)"
-    CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
-    if (int rc = exchange(u, T)) return rc;  // exchange(0): the only one not hidden
-    bool first = true;
-    while (left > 0) {
-        bool launched = false;
-        if (!first) CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));  // interior(n-1) done
-        CSIM_CUDA(cudaEventRecord(c->ev_go, c->stream_x));                       // go(n)
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched, zero_terms)) return rc;
-        CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));                     // frame(n) done
-        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_go, 0));
-        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_INTERIOR, c->stream, &launched, zero_terms)) return rc;
-        CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));                       // interior(n) done
-        tmp->values = values_after;
-        csim_field_swap(u, tmp);
-        left -= T;
-        first = false;
-        if (left > 0) {
-            T = left < maxT ? left : maxT;
-            if (int rc = exchange(u, T)) return rc;  // exchange(n+1): reads frame(n)'s cells
-        }
+    if (nsteps == 0) return CSIM_OK;
+    if (int rc = ensure_wide(c, u, dec, maxT)) return rc;
+    RunState* rs = run_state(c);
+    int swaps = 0;
+    if (rs->prof.on) {  // profiled call: eager, with timestamps (csim_halo_profile)
+        rs->prof.used = 0;
+        rs->prof.blocks = 0;
+        CSIM_CUDA(cudaEventRecord(rs->prof.next(c), c->stream));  // time base
+        if (int rc = enqueue_blocks(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, &rs->prof, &swaps))
+            return rc;
+        rs->comm_warm = true;
+        return finish_profile(c, rs);
     }
-    CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the main stream orders everything again
+    // The block loop is ~8 launches per block (pack, NCCL group, unpack, frame, interior + events): at
+    // 34 blocks per 100 steps the host spent as long enqueueing them as the GPUs spent running them
+    // (round 1: 7.4 ms against 7.9 ms at 8192^2 per GPU).  So the loop is captured into a CUDA graph the
+    // first time a (tiles, parameters, step count) combination is seen and replayed afterwards; the
+    // very first call of a communicator runs eagerly, because NCCL sets up its connections to the
+    // neighbours on first use, which must not happen inside a capture.  CSIM_GRAPH=0 disables it.
+    static const bool graphs_on = [] {
+        const char* e = std::getenv("CSIM_GRAPH");
+        return !(e && std::strcmp(e, "0") == 0);
+    }();
+    if (!graphs_on || !rs->comm_warm) {
+        if (int rc = enqueue_blocks(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, nullptr, &swaps))
+            return rc;
+        rs->comm_warm = true;
+        return CSIM_OK;
+    }
+    RunKey key;
+    std::memset(&key, 0, sizeof key);  // padding bytes take part in the comparison
+    key.u = u->base;
+    key.tmp = tmp->base;
+    key.nsteps = nsteps;
+    key.maxT = maxT;
+    key.mode = mode;
+    key.zero_terms = zero_terms ? 1 : 0;
+    std::memcpy(&key.p, p, sizeof key.p);
+    std::memcpy(&key.d, dec, sizeof key.d);
+    ++rs->tick;
+    for (RunGraph& g : rs->graphs)
+        if (same_key(g.key, key)) {
+            CSIM_CUDA(cudaGraphLaunch(g.exec, c->stream));
+            g.last_use = rs->tick;
+            c->launches += g.launches;
+            if (g.swaps & 1) csim_field_swap(u, tmp);
+            u->values = values_after;  // the newest state was written by the sweep
+            return CSIM_OK;
+        }
+    const uint64_t launches0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    CSIM_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_blocks(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, nullptr, &swaps);
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != CSIM_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture(csim_run_steps)", __FILE__, __LINE__);
+    RunGraph g;
+    g.key = key;
+    g.launches = c->launches - launches0;
+    g.swaps = swaps;
+    g.last_use = rs->tick;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return cuda_fail(ie, "cudaGraphInstantiate(csim_run_steps)", __FILE__, __LINE__);
+    if (rs->graphs.size() >= 16) {  // keep the cache small: drop the least recently used graph
+        size_t victim = 0;
+        for (size_t i = 1; i < rs->graphs.size(); ++i)
+            if (rs->graphs[i].last_use < rs->graphs[victim].last_use) victim = i;
+        cudaGraphExecDestroy(rs->graphs[victim].exec);
+        rs->graphs.erase(rs->graphs.begin() + static_cast<long>(victim));
+    }
+    rs->graphs.push_back(g);
+    CSIM_CUDA(cudaGraphLaunch(g.exec, c->stream));  // the capture recorded the work; this runs it
+    return CSIM_OK;
+}
+
+int csim_halo_profile(csim_ctx* c, int enable) {
+    CSIM_REQUIRE(c != nullptr, CSIM_ERR_INVALID, "csim_halo_profile: ctx is null");
+    run_state(c)->prof.on = enable != 0;
+    return CSIM_OK;
+}
+
+int csim_halo_stats_get(csim_ctx* c, csim_halo_stats* out) {
+    CSIM_REQUIRE(c != nullptr && out != nullptr, CSIM_ERR_INVALID, "csim_halo_stats_get: null argument");
+    *out = run_state(c)->last;
     return CSIM_OK;
 }
 

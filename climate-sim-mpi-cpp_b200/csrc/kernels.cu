@@ -408,35 +408,25 @@ int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k,
     return CSIM_OK;
 }
 
-cudaError_t tb_launch(int vxs, int vys, int kind, int T, int mode, const TbArgs& a, cudaStream_t stream) {
+cudaError_t tb_launch(int vxs, int vys, int T, int mode, const TbArgs& a, cudaStream_t stream) {
     switch ((vxs + 1) * 3 + (vys + 1)) {
-        case 0: return tb_launch_nn(kind, T, mode, a, stream);
-        case 1: return tb_launch_nz(kind, T, mode, a, stream);
-        case 2: return tb_launch_np(kind, T, mode, a, stream);
-        case 3: return tb_launch_zn(kind, T, mode, a, stream);
-        case 4: return tb_launch_zz(kind, T, mode, a, stream);
-        case 5: return tb_launch_zp(kind, T, mode, a, stream);
-        case 6: return tb_launch_pn(kind, T, mode, a, stream);
-        case 7: return tb_launch_pz(kind, T, mode, a, stream);
-        default: return tb_launch_pp(kind, T, mode, a, stream);
+        case 0: return tb_launch_nn(T, mode, a, stream);
+        case 1: return tb_launch_nz(T, mode, a, stream);
+        case 2: return tb_launch_np(T, mode, a, stream);
+        case 3: return tb_launch_zn(T, mode, a, stream);
+        case 4: return tb_launch_zz(T, mode, a, stream);
+        case 5: return tb_launch_zp(T, mode, a, stream);
+        case 6: return tb_launch_pn(T, mode, a, stream);
+        case 7: return tb_launch_pz(T, mode, a, stream);
+        default: return tb_launch_pp(T, mode, a, stream);
     }
-}
-
-static int tb_kernel_kind() {
-    // kind 1 = k_step_tb (two rows per tick), the default; CSIM_TB_KERNEL=ring selects k_step_ring
-    // (one row per tick, rotating ring of row slots), which is parity-tested and kept for A/B timing
-    static const int kind = [] {
-        const char* e = std::getenv("CSIM_TB_KERNEL");
-        return (e && std::strcmp(e, "ring") == 0) ? 0 : 1;
-    }();
-    return kind;
 }
 
 // Geometry of one sweep: which cells are advanced / stored / need no boundary fix-up, and how the
 // tile is cut into (strip, chunk) work items.  Pure host arithmetic (csim_sweep_plan exposes it to the
 // CPU tests).  phys: bit s set = side s is a physical boundary; slots: resident warps of the machine.
 // Returns false when the requested part has no work item.
-static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int slots, int kind, int part, TbArgs& a) {
+static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int slots, int part, TbArgs& a) {
     a.pitch = pitch;
     a.nx = nx;
     a.ny = ny;
@@ -456,9 +446,8 @@ static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int sl
     a.fy1 = pt ? ny - 1 : a.yhi;
     a.xmax_load = static_cast<int>(pitch) - kLeadX;
     a.pf_rows = tb_env_int("CSIM_TB_PF", 4);
-    a.row_limit = a.pf_rows > 0 ? ny + kLeadY : -(1 << 30);  // <= 0 disables the prefetch branch
-    if (a.pf_rows < 0) a.pf_rows = 0;
-    a.pf_off = static_cast<long long>(a.pf_rows) * pitch;
+    a.pf_off = static_cast<long long>(a.pf_rows > 0 ? a.pf_rows : 0) * pitch;
+    if (a.pf_rows <= 0) a.pf_rows = 1 << 29;  // off: r + 3 + pf_rows < r_end never holds
     a.nstrips = (nx + kTbWout - 1) / kTbWout;
     if (a.nstrips < 1) a.nstrips = 1;
     a.edge_split = tb_env_int("CSIM_TB_EDGE_SPLIT", 2);
@@ -469,32 +458,15 @@ static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int sl
     const int weight = n_int + n_edge * a.edge_split;
     // Chunk height.  A launch runs as several rounds of resident warps; short chunks keep the last
     // round from idling the machine, tall chunks amortise the 2T rows each chunk re-computes.
-    // Measured on B200 at 8192^2 (profiles/r01_tb_tuning.md): 64-128 rows is the flat optimum.
+    // Measured on B200: at 8192^2 64-128 rows is the flat optimum (profiles/r01_tb_tuning.md); at
+    // 16384^2, with four times the items, 192-384 rows gain 3-4 % over 96 (profiles/r02_tuning.md).
+    // So: at least four rounds of resident warps, at most 384 rows.
     int ch = tb_env_int("CSIM_TB_CHUNK", 0);
     if (ch <= 0) {
-        const long long want = static_cast<long long>(rows) * weight / (2LL * slots);  // >= 2 rounds
-        ch = static_cast<int>(want < 32 ? 32 : (want > 96 ? 96 : want));
-        if (kind == 0) {
-            // k_step_ring runs its hot code in groups of N = 2T+3 ticks and a chunk of h rows takes
-            // h + 2T ticks: pick h so that the groups tile the chunk exactly, and among those heights
-            // the one with the least (rounds of resident warps) x (ticks per chunk)
-            const int N = CSIM_RING_U < ring_slots(T) ? CSIM_RING_U : ring_slots(T);
-            long long best_cost = -1;
-            for (int m = 4; m <= 64; ++m) {
-                const int hc = m * N - 2 * T;
-                if (hc < 32 || hc > 160) continue;
-                const long long nch = (rows + hc - 1) / hc;
-                const long long items = nch * n_int + ((rows + (hc + a.edge_split - 1) / a.edge_split - 1) /
-                                                       ((hc + a.edge_split - 1) / a.edge_split)) * n_edge;
-                const long long rounds = (items + slots - 1) / slots;
-                // a partly filled last round still costs a whole chunk time
-                const long long cost = rounds * (hc + 2 * T);
-                if (best_cost < 0 || cost < best_cost) {
-                    best_cost = cost;
-                    ch = hc;
-                }
-            }
-        }
+        static const int ch_max = tb_env_int("CSIM_TB_CHUNK_MAX", 384);
+        static const int min_rounds = tb_env_int("CSIM_TB_ROUNDS", 4);
+        const long long want = static_cast<long long>(rows) * weight / (static_cast<long long>(min_rounds > 0 ? min_rounds : 1) * slots);
+        ch = static_cast<int>(want < 32 ? 32 : (want > ch_max ? ch_max : want));
     }
     if (ch > rows) ch = rows;
     if (ch < 1) ch = 1;
@@ -571,17 +543,16 @@ static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int sl
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
                    int T, int part, cudaStream_t stream, bool* launched, bool zero_terms) {
     csim_ctx* c = u->ctx;
-    const int kind = tb_kernel_kind();
     TbArgs a;
     a.u = u->interior();
     a.out = out->interior();
+    a.out_minus_u = reinterpret_cast<const char*>(a.out) - reinterpret_cast<const char*>(a.u);
     int phys = 0;
     for (int s = 0; s < 4; ++s)
         if (p->nbr[s] == CSIM_PROC_NULL) phys |= 1 << s;
     if (launched) *launched = false;
-    const int slots =
-        c->sm_count * (kind == 0 ? kRingBlocksPerSM * kRingWarpsPerBlock : kTbBlocksPerSM * kTbWarpsPerBlock);
-    if (!tb_geometry(u->nx, u->ny, u->pitch, T, phys, slots, kind, part, a)) return CSIM_OK;
+    const int slots = c->sm_count * kTbBlocksPerSM * kTbWarpsPerBlock;
+    if (!tb_geometry(u->nx, u->ny, u->pitch, T, phys, slots, part, a)) return CSIM_OK;
     a.bcL = p->bc[0];
     a.bcR = p->bc[1];
     a.bcB = p->bc[2];
@@ -596,7 +567,7 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
         if (is_pos_zero(k.vx)) vxs = 0;
         if (is_pos_zero(k.vy)) vys = 0;
     }
-    const cudaError_t e = tb_launch(vxs, vys, kind, T, mode, a, stream);
+    const cudaError_t e = tb_launch(vxs, vys, T, mode, a, stream);
     ++c->launches;
     if (e != cudaSuccess) return cuda_fail(e, "k_step_tb", __FILE__, __LINE__);
     return CSIM_OK;
@@ -751,12 +722,11 @@ int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps,
     int phys = 0;
     for (int s = 0; s < 4; ++s)
         if (nbr[s] == CSIM_PROC_NULL) phys |= 1 << s;
-    const int kind = tb_kernel_kind();
     const int slots = resident_warps > 0 ? resident_warps : 148 * kTbBlocksPerSM * kTbWarpsPerBlock;
     const long long pitch = (static_cast<long long>(kLeadX) + nx + kTailX + 15) / 16 * 16;
     TbArgs a;
     *count = 0;
-    if (!tb_geometry(nx, ny, pitch, T, phys, slots, kind, part, a)) return CSIM_OK;
+    if (!tb_geometry(nx, ny, pitch, T, phys, slots, part, a)) return CSIM_OK;
     int n = 0;
     for (int item = 0; item < a.n_items; ++item) {
         int strip, ya, yb;

@@ -43,6 +43,7 @@ enum { MODE_UNIT = 0, MODE_RECIP = 1, MODE_DIV = 2 };
 struct TbArgs {
     const double* u;   // level-0 field, pointer to interior cell (0,0)
     double* out;       // level-T field, pointer to interior cell (0,0)
+    long long out_minus_u;  // byte distance from a cell of u to the same cell of out
     long long pitch;   // doubles per row
     int nx, ny;        // interior size of the tile
     int xlo, xhi, ylo, yhi;  // cells advanced by the stencil: xlo<=x<xhi, ylo<=y<yhi
@@ -59,9 +60,8 @@ struct TbArgs {
     int int_chunk0;    // interior strips: first chunk enumerated ...
     int frame_pair;    // ... or, if set, exactly the first and the last chunk of every interior strip
     int xmax_load;     // a lane may load its 4 cells iff x0+3 < xmax_load (row allocation bound)
-    int pf_rows;       // L2 prefetch distance in rows (0 = off)
+    int pf_rows;       // L2 prefetch distance in rows (off: a huge distance, which no row guard passes)
     long long pf_off;  // pf_rows * pitch
-    int row_limit;     // rows y < row_limit are inside the allocation
     int phys;          // bit s: side s (left,right,bottom,top) is a physical boundary
     int bcL, bcR, bcB, bcT;
     double value;      // Dirichlet value
@@ -150,21 +150,29 @@ struct TbLane {
     int ghost_r;   // index of the cell with x == nx   on a physical right side, or -1
 };
 
+// The three flavours of a tick.  TICK_FAST: the plain stencil on all four cells (interior strips,
+// interior rows).  TICK_XMASK: interior rows of a strip that touches a side whose ghost cells are
+// merely frozen or advanced like interior cells (a "periodic" physical side, SURVEY.md Q1/Q2, or a
+// side with a neighbour): the plain stencil, then cells outside [xlo, xhi) keep their value.
+// TICK_GEN: every boundary rule of the reference (see the file header); all conditions on j are
+// warp-uniform, all conditions on x are per-lane selects, so the four stencils still interleave.
+enum { TICK_FAST = 0, TICK_XMASK = 1, TICK_GEN = 2 };
+
 // One row of one level.  s/c/n are rows j-1, j, j+1 of the current level; the result is row j of
-// the next level.  GEN = false: the plain stencil on all four cells (interior strips, interior
-// rows).  GEN = true: every boundary rule of the reference (see the file header); all conditions on
-// j are warp-uniform, all conditions on x are per-lane selects, so the four stencils still
-// interleave.
-template <int MODE, int VXS, int VYS, bool GEN>
+// the next level.
+template <int MODE, int VXS, int VYS, int KIND>
 __device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j, const double (&s)[4],
                                        const double (&c)[4], const double (&n)[4], double (&res)[4]) {
     const double w0 = __shfl_up_sync(0xffffffffu, c[3], 1);
     const double e3 = __shfl_down_sync(0xffffffffu, c[0], 1);
-    if (!GEN) {
-        res[0] = tb_update<MODE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k);
-        res[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k);
-        res[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k);
-        res[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k);
+    if (KIND != TICK_GEN) {
+        double r[4];
+        r[0] = tb_update<MODE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k);
+        r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k);
+        r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k);
+        r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res[i] = (KIND == TICK_FAST || ((ln.inx >> i) & 1)) ? r[i] : c[i];
         return;
     }
     const bool physB = a.phys & 4, physT = a.phys & 8;
@@ -259,10 +267,14 @@ __device__ __forceinline__ void tb_store_row(const TbArgs& a, const TbLane& ln, 
 // state (rows r-k-2, r-k-1) and slot 1-PH its incoming pair (rows r-k, r-k+1); afterwards the
 // incoming pair is the state and slot PH is free for the next pair, so consecutive ticks alternate PH
 // and no register is ever moved.
-template <int T, int MODE, int VXS, int VYS, int PH, bool GEN>
+// Rows are counted twice: `r` is the absolute row (boundary rules of the general ticks), `q` = r-T-ya
+// is the first finished row relative to the work item, which has `h` rows.  Fast ticks use only q and
+// h (store window 0 <= q < h, request window q+2 < h) and derive the store address from the load
+// pointer, so their loop carries neither r, ya, yb nor a second pointer.
+template <int T, int MODE, int VXS, int VYS, int PH, int KIND>
 __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int lane, bool lane_store_all,
-                                        bool can_load, int r, int ya, int yb, const double*& src, double*& dst,
-                                        double (&st)[T][2][2][4]) {
+                                        bool can_load, int r, int q, int h, int ya, int yb,
+                                        const double*& src, double (&st)[T][2][2][4]) {
     double fin[2][4];
 #pragma unroll
     for (int k = 0; k < T; ++k) {
@@ -271,37 +283,51 @@ __device__ __forceinline__ void tb_tick(const TbArgs& a, const TbLane& ln, int l
         double(&C)[4] = st[k][1 - PH][0];
         double(&D)[4] = st[k][1 - PH][1];
         if (k + 1 < T) {
-            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k - 1, A, B, C, st[k + 1 < T ? k + 1 : k][1 - PH][0]);
-            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k, B, C, D, st[k + 1 < T ? k + 1 : k][1 - PH][1]);
+            tb_row<MODE, VXS, VYS, KIND>(a, ln, r - k - 1, A, B, C, st[k + 1 < T ? k + 1 : k][1 - PH][0]);
+            tb_row<MODE, VXS, VYS, KIND>(a, ln, r - k, B, C, D, st[k + 1 < T ? k + 1 : k][1 - PH][1]);
         } else {
-            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k - 1, A, B, C, fin[0]);
-            tb_row<MODE, VXS, VYS, GEN>(a, ln, r - k, B, C, D, fin[1]);
+            tb_row<MODE, VXS, VYS, KIND>(a, ln, r - k - 1, A, B, C, fin[0]);
+            tb_row<MODE, VXS, VYS, KIND>(a, ln, r - k, B, C, D, fin[1]);
         }
         if (k == 0) {
-            // rows r-2, r-1 of level 0 are dead now: prefetch rows r+2, r+3 into their registers.
-            // Fast ticks run only in strips that lie inside the row allocation with all 32 lanes
-            // (strip_fast implies xb + 128 <= nx + T < xmax_load), so their loads are unconditional.
-            const bool ld = GEN ? can_load : true;
-            tb_load4(src, ld, A);
-            tb_load4(src + a.pitch, ld, B);
-            // pull the rows pf_rows ahead into L2 (costs no registers; clamped to the allocation)
-            if (ld && r + 3 + a.pf_rows < a.row_limit) {
+            // rows r-2, r-1 of level 0 are dead now: request rows r+2, r+3 into their registers.  The
+            // last level-0 row a work item needs is yb+T-1 <= ny+T (r+2 < yb+T  <=>  q+2 < h); past it the
+            // fast ticks re-read rows 0 and 1 of their own columns instead — an address that is always
+            // inside the allocation and resident in L2 — so that the load itself stays unconditional:
+            // a predicated or branched-around load makes ptxas land the rows in temporaries and move them
+            // within the same tick, which stalls the warp for a DRAM round trip (35 % of all stall
+            // samples in profiles/r02a).  The values feed rows nobody stores.  Fast ticks run only in
+            // strips that lie inside the row allocation with all 32 lanes (strip_fast implies
+            // xb + 128 <= nx + T < xmax_load).
+            const bool rows_needed = q + 2 < h;
+            if (KIND != TICK_FAST) {
+                tb_load4(src, can_load && rows_needed, A);
+                tb_load4(src + a.pitch, can_load && rows_needed, B);
+            } else {
+                const double* ls = rows_needed ? src : a.u + ln.x0;
+                tb_load4(ls, true, A);
+                tb_load4(ls + a.pitch, true, B);
+            }
+            // pull the rows pf_rows ahead into L2 (costs no registers; never past the rows the item reads)
+            if ((KIND != TICK_FAST ? can_load : true) && q + 3 + a.pf_rows < h) {
                 tb_prefetch_l2(src + a.pf_off);
                 tb_prefetch_l2(src + a.pf_off + a.pitch);
             }
             src += 2 * a.pitch;
         }
     }
-    if (!GEN) {
+    if (KIND == TICK_FAST) {
         // fast ticks run only in strips where every lane stores all four cells or none, and the rows
-        // they finish are interior rows: one predicated 256-bit store per row, no per-cell tests
-        if (lane_store_all && r - T >= ya && r - T < yb) tb_store4(dst, fin[0]);
-        if (lane_store_all && r - T + 1 >= ya && r - T + 1 < yb) tb_store4(dst + a.pitch, fin[1]);
+        // they finish are interior rows: one predicated 256-bit store per row, no per-cell tests.
+        // src points at row r+4 of `u` by now; row r-T of `out` lies a fixed (warp-uniform) distance away.
+        double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(const_cast<double*>(src)) + a.out_minus_u) -
+                      (T + 4) * a.pitch;
+        if (lane_store_all && q >= 0 && q < h) tb_store4(dst, fin[0]);
+        if (lane_store_all && q + 1 >= 0 && q + 1 < h) tb_store4(dst + a.pitch, fin[1]);
     } else {
         tb_store_row(a, ln, lane, lane_store_all, r - T, ya, yb, fin[0]);
         tb_store_row(a, ln, lane, lane_store_all, r - T + 1, ya, yb, fin[1]);
     }
-    dst += 2 * a.pitch;  // row r-T of `out` at this lane's columns, kept incrementally like src
 }
 
 template <int T, int MODE, int VXS, int VYS>
@@ -323,6 +349,10 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     const bool lane_partial = !lane_store_all && lane >= 1 && lane <= 30 && ln.x0 + 3 >= a.sx0 && ln.x0 < a.sx1;
     const bool strip_fast =
         xb >= a.fx0 && xb + kTbWidth <= a.fx1 && __ballot_sync(0xffffffffu, lane_partial) == 0u;
+    // the strip touches no Dirichlet/Neumann column: its interior rows need the cell mask only
+    const bool strip_xmask = !(((a.phys & 1) && a.bcL != 2 && xb <= 0) ||
+                               ((a.phys & 2) && a.bcR != 2 && xb + kTbWidth >= a.nx));
+    const int mid = strip_fast ? TICK_FAST : (strip_xmask ? TICK_XMASK : TICK_GEN);
     {
         const bool physL = a.phys & 1, physR = a.phys & 2;
         ln.inx = 0;
@@ -347,19 +377,37 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
     tb_load4(src, can_load, st[0][1][0]);
     tb_load4(src + a.pitch, can_load, st[0][1][1]);
     src += 2 * a.pitch;
-    double* dst = a.out + static_cast<long long>(r - T) * a.pitch + ln.x0;  // first tick finishes rows r-T, r-T+1
 
-    // every tick touches rows r-T .. r+1; it is "fast" when all rows it produces are interior
+    // A loop iteration is two ticks (phases 0 and 1) and touches rows r-T .. r+3.  Iterations whose rows
+    // are all plain interior rows run as an inner loop of the strip's flavour (TICK_FAST or TICK_XMASK);
+    // the fast one carries nothing but a row counter, the item height and the load pointer, and
+    // everything the general ticks need (boundary flags, per-lane masks) stays out of its registers.
+    const int h = yb - ya;
     const int r_end = yb + T;
-    for (; r < r_end; r += 4) {
-        if (strip_fast && r - T >= a.fy0 && r < a.fy1)
-            tb_tick<T, MODE, VXS, VYS, 0, false>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, dst, st);
-        else
-            tb_tick<T, MODE, VXS, VYS, 0, true>(a, ln, lane, lane_store_all, can_load, r, ya, yb, src, dst, st);
-        if (strip_fast && r + 2 - T >= a.fy0 && r + 2 < a.fy1)
-            tb_tick<T, MODE, VXS, VYS, 1, false>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, dst, st);
-        else
-            tb_tick<T, MODE, VXS, VYS, 1, true>(a, ln, lane, lane_store_all, can_load, r + 2, ya, yb, src, dst, st);
+    while (r < r_end) {
+        if (mid != TICK_GEN && r - T >= a.fy0 && r + 2 < a.fy1) {
+            // iterations until the first one that would touch row fy1 or lie beyond the chunk
+            int n_it = (min(a.fy1 - 2, r_end) - r + 3) >> 2;
+            if (mid == TICK_FAST) {
+                int q = r - T - ya;
+                r += 4 * n_it;
+#pragma unroll 1
+                for (; n_it > 0; --n_it, q += 4) {
+                    tb_tick<T, MODE, VXS, VYS, 0, TICK_FAST>(a, ln, lane, lane_store_all, true, 0, q, h, 0, 0, src, st);
+                    tb_tick<T, MODE, VXS, VYS, 1, TICK_FAST>(a, ln, lane, lane_store_all, true, 0, q + 2, h, 0, 0, src, st);
+                }
+            } else {
+#pragma unroll 1
+                for (; n_it > 0; --n_it, r += 4) {
+                    tb_tick<T, MODE, VXS, VYS, 0, TICK_XMASK>(a, ln, lane, lane_store_all, can_load, r, r - T - ya, h, ya, yb, src, st);
+                    tb_tick<T, MODE, VXS, VYS, 1, TICK_XMASK>(a, ln, lane, lane_store_all, can_load, r + 2, r + 2 - T - ya, h, ya, yb, src, st);
+                }
+            }
+        } else {
+            tb_tick<T, MODE, VXS, VYS, 0, TICK_GEN>(a, ln, lane, lane_store_all, can_load, r, r - T - ya, h, ya, yb, src, st);
+            tb_tick<T, MODE, VXS, VYS, 1, TICK_GEN>(a, ln, lane, lane_store_all, can_load, r + 2, r + 2 - T - ya, h, ya, yb, src, st);
+            r += 4;
+        }
     }
 }
 

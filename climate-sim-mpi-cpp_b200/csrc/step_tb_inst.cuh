@@ -5,36 +5,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "step_ring.cuh"
 #include "step_tb.cuh"
 
 namespace csim {
 
-// kind 1: k_step_tb   (two rows per tick, four rows per level — the default);
-// kind 0: k_step_ring (one row per tick, ring of 2T+3 row slots — CSIM_TB_KERNEL=ring)
-// k_step_ring keeps kRingStages rows per warp in shared memory; ask for the large carve-out once per
-// instantiation so that four CTAs (128 KB) fit on an SM
-template <int T, int MODE, int VXS, int VYS>
-cudaError_t ring_launch(const TbArgs& a, cudaStream_t stream) {
-    const dim3 block(32 * kRingWarpsPerBlock);
-    const dim3 grid((a.n_items + kRingWarpsPerBlock - 1) / kRingWarpsPerBlock);
-    static const cudaError_t prepared = cudaFuncSetAttribute(
-        k_step_ring<T, MODE, VXS, VYS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (prepared != cudaSuccess) return prepared;
-    k_step_ring<T, MODE, VXS, VYS><<<grid, block, kRingSmemBytes, stream>>>(a);
-    return cudaGetLastError();
-}
-
 template <int VXS, int VYS>
-cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStream_t stream) {
+cudaError_t tb_launch_signed(int T, int mode, const TbArgs& a, cudaStream_t stream) {
     const dim3 block(32 * kTbWarpsPerBlock);
     const dim3 grid((a.n_items + kTbWarpsPerBlock - 1) / kTbWarpsPerBlock);
 #define CSIM_TB_CASE(TT, MM)                                                  \
     if (T == TT && mode == MM) {                                              \
-        if (kind == 0)                                                        \
-            return ring_launch<TT, MM, VXS, VYS>(a, stream);                  \
-        else                                                                  \
-            k_step_tb<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);       \
+        k_step_tb<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);           \
         return cudaGetLastError();                                            \
     }
     if (VXS != 0 && VYS != 0) {
@@ -60,11 +41,11 @@ cudaError_t tb_launch_signed(int kind, int T, int mode, const TbArgs& a, cudaStr
 }
 
 // vxs, vys in {-1, 0, +1}
-cudaError_t tb_launch(int vxs, int vys, int kind, int T, int mode, const TbArgs& a, cudaStream_t stream);
+cudaError_t tb_launch(int vxs, int vys, int T, int mode, const TbArgs& a, cudaStream_t stream);
 bool tb_has_zero_variant(int T, int mode);
 
 #define CSIM_DECLARE_LAUNCH(name) \
-    cudaError_t tb_launch_##name(int kind, int T, int mode, const TbArgs& a, cudaStream_t stream);
+    cudaError_t tb_launch_##name(int T, int mode, const TbArgs& a, cudaStream_t stream);
 CSIM_DECLARE_LAUNCH(pp) CSIM_DECLARE_LAUNCH(pn) CSIM_DECLARE_LAUNCH(np) CSIM_DECLARE_LAUNCH(nn)
 CSIM_DECLARE_LAUNCH(pz) CSIM_DECLARE_LAUNCH(nz) CSIM_DECLARE_LAUNCH(zp) CSIM_DECLARE_LAUNCH(zn)
 CSIM_DECLARE_LAUNCH(zz)

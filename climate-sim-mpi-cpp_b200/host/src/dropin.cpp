@@ -248,16 +248,7 @@ void run_timesteps(Field& u, Field& tmp, const Decomp2D& dec, const BCConfig& bc
     p.flags = 0;
     csim_field* du = u.data.device_rw();
     csim_field* dt_ = tmp.data.device_rw();
-    // more than one rank: halos travel as packed bands over grouped NCCL send/recv (the faster path
-    // with the current sweep, profiles/r01b_weak_scaling.md); CSIM_HALO=p2p maps the neighbours' tiles
-    // once so that they travel as direct NVLink stores instead
-    static csim_field* mapped[2] = {nullptr, nullptr};
-    if (csim_host::world().size > 1 && (mapped[0] != du || mapped[1] != dt_)) {
-        const char* h = std::getenv("CSIM_HALO");
-        if (h && std::strcmp(h, "p2p") == 0) check(csim_peer_setup(du, dt_, &c));
-        mapped[0] = du;
-        mapped[1] = dt_;
-    }
+    // more than one rank: halos travel as packed T-line bands over grouped NCCL send/recv
     // csim_run_steps swaps the device buffers of the two tiles an odd or even number of times; the
     // newest state ends up in u's handle either way.
     check(csim_run_steps(du, dt_, &p, &c, nsteps));

@@ -42,8 +42,8 @@ typedef enum csim_status {
     CSIM_ERR_NOMEM = 3,       /* host or device allocation failed                              */
     CSIM_ERR_RANGE = 4,       /* index outside the padded tile (Field::at → std::out_of_range) */
     CSIM_ERR_UNSUPPORTED = 5, /* valid in the reference, not on this path (e.g. halo != 1)     */
-    CSIM_ERR_COMM = 6,        /* NCCL / peer-memory failure                                    */
-    CSIM_ERR_TIMEOUT = 7      /* a neighbour's halo did not arrive within the bounded wait     */
+    CSIM_ERR_COMM = 6,        /* NCCL failure                                                  */
+    CSIM_ERR_TIMEOUT = 7      /* reserved (was: bounded wait of the removed peer-push halo)    */
 } csim_status;
 
 /* enum class BCType { Dirichlet, Neumann, Periodic } — reference include/boundary.hpp:5 */
@@ -226,20 +226,6 @@ int csim_comm_allreduce_max(csim_ctx* ctx, double* inout, int n);
  * over NVLink, and unpacked by a kernel; all on the context stream. */
 int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
 
-/* Peer-memory halo path (collective over the communicator; call once after csim_comm_init with the
- * two tiles csim_run_steps will be given).  Every rank maps its up to eight neighbours' tiles and
- * flag words into its own address space (CUDA IPC between processes, peer access inside one
- * process).  csim_run_steps then replaces pack → NCCL → unpack by ONE kernel whose CTAs store this
- * rank's edge bands straight into the neighbours' ghost lines over NVLink and raise a flag there; the
- * neighbour's frame sweep is gated by a bounded wait on that flag (CSIM_ERR_TIMEOUT, never a hang).
- * Without this call, or with CSIM_HALO=nccl in the environment, the NCCL path is used — which is what
- * bench.py and the C++ drop-in do by default: with the round-1b sweep the NCCL path measured faster at
- * 2, 4 and 8 GPUs (profiles/r01b_weak_scaling.md); CSIM_HALO=p2p opts into this path there.
- * Call csim_peer_teardown on every rank (after a barrier) before destroying the tiles; destroying a
- * mapped tile also takes this rank's links down. */
-int csim_peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec);
-int csim_peer_teardown(csim_ctx* ctx);
-
 /* One region of the wide (T-line, 8-neighbour) exchange csim_run_steps performs per T-step block:
  * interior coordinates of its first cell, extent, and the rank on the other side (-1: no such
  * neighbour).  Index k enumerates directions (dx,dy) row by row from (-1,-1) to (1,1) without (0,0). */
@@ -275,6 +261,23 @@ int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps,
  * fields bit-identical. */
 int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p,
                    const csim_decomp* dec, int nsteps);
+
+/* Timeline of the multi-rank block loop (diagnostic; bench.py's halo report).  After
+ * csim_halo_profile(ctx, 1) the NEXT csim_run_steps call on a tile with neighbours runs eagerly (no graph
+ * replay), with CUDA-event timestamps around every exchange, frame sweep and interior sweep, waits for
+ * completion and leaves the figures here; profiling switches itself off again. */
+typedef struct csim_halo_stats {
+    int blocks;                /* T-step blocks of the profiled call                                    */
+    size_t bytes_per_exchange; /* bytes this rank SENDS per exchange (8 regions of T lines; as many come in) */
+    double first_exchange_us;  /* exchange(0): pack + NCCL group + unpack, nothing to hide behind       */
+    double exchange_us;        /* mean duration of the later exchanges (each runs beside an interior sweep) */
+    double overlap_fraction;   /* share of that time that lies inside the concurrent interior sweep     */
+    double frame_us;           /* mean frame sweep (edge strips + first/last chunks: the ghost-line readers) */
+    double interior_us;        /* mean interior sweep                                                   */
+    double total_ms;           /* first to last timestamp of the call                                   */
+} csim_halo_stats;
+int csim_halo_profile(csim_ctx* ctx, int enable);
+int csim_halo_stats_get(csim_ctx* ctx, csim_halo_stats* out);
 
 /* gaussian_hotspot / constant_zero initial condition on the host tile — src/init.cpp:12-47.
  * Computed with the host libm's exp() so it is bit-identical to the reference's; writes the

@@ -1,6 +1,7 @@
 """One rank of a torchrun-launched parity run (used by tests/test_gpu_parity.py): every rank advances
-its tile through csim_run_steps with the peer-memory (CUDA IPC) or NCCL halo path; rank 0 gathers the
-tiles and compares the global field with the single-rank CPU oracle, bit for bit."""
+its tile through csim_run_steps (packed bands over grouped NCCL send/recv) twice — the second pass
+replays the CUDA graph the first one captured — and rank 0 gathers the tiles and compares the global
+field with the single-rank CPU oracle, bit for bit."""
 import importlib
 import os
 import sys
@@ -26,13 +27,11 @@ def main():
     cases = [(1000, 700, (7, 3, 1, 5), (0.05, 0.5, -0.3, 0.1), (2, 2, 2, 2)),
              (777, 1301, (10, 4), (0.05, -0.4, -0.2, 0.1), (1, 0, 1, 2))]
     for (nxg, nyg, steps, phys, bc) in cases:
-        for path in ("p2p", "nccl"):
+        for path in ("captured", "replayed"):
             dec = csim.Decomp2D.init(world, rank, nxg, nyg)
             u = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
             tmp = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
             u.upload(csim.initial_condition_host(dec, 1, 1.0, 1.0))
-            if path == "p2p":
-                csim.peer_setup(u, tmp, dec)
             p = csim.make_step_params(*phys, csim.BCConfig(*[csim.BCType(b) for b in bc]), dec)
             for k in steps:
                 csim.run_steps(u, tmp, p, dec, k)
@@ -51,8 +50,7 @@ def main():
                 same = np.array_equal(glob.view(np.uint64), want.view(np.uint64))
                 print(f"mp_parity {path} {nxg}x{nyg} world={world}: {'OK' if same else 'MISMATCH'}", flush=True)
                 ok = ok and same
-            dist.barrier()  # nobody frees a tile a neighbour may still be pushing into
-            csim.peer_teardown(ctx)
+            dist.barrier()
             u.close()
             tmp.close()
             dist.barrier()

@@ -144,6 +144,31 @@ def test_sweep_plan_tiles_the_stored_region_exactly_once(csim, nx, ny):
                     assert len(whole) >= slots  # enough items to fill the machine at least once
 
 
+def test_sweep_items_load_only_rows_inside_the_allocation(csim):
+    """Load model of k_step_tb (step_tb.cuh): a work item [y0, y1) starts with level-0 rows y0-T and
+    y0-T+1, and every tick at row r (two per loop iteration, r advancing by 2) requests rows r+2 and r+3
+    iff r+2 < y1+T.  Every row it touches must lie inside the kLeadY = 8 rows of padding below and
+    above the tile (csim_field_create allocates ny + 16 rows) — also at T = 4, with physical top and
+    bottom sides (stored range -1 … ny) and with chunk heights that are 3 mod 4."""
+    lead = 8
+    rng = np.random.default_rng(2718)
+    sizes = [(1, 1), (5, 3), (256, 256), (512, 512), (1024, 1024), (4096, 4096), (16352, 16384), (130, 4099)]
+    sizes += [(int(rng.integers(1, 600)), int(rng.integers(1, 3000))) for _ in range(40)]
+    for (nx, ny) in sizes:
+        for T in (1, 2, 3, 4):
+            for nbr in ((-1, -1, -1, -1), (1, 2, 3, 4), (-1, 2, -1, 4)):
+                for (_s, _x0, _x1, y0, y1) in csim.sweep_plan(nx, ny, T, nbr, 1776, 0):
+                    r_end = y1 + T
+                    lo, hi = y0 - T, y0 - T + 1
+                    r = y0 - T
+                    while r < r_end:          # for (; r < r_end; r += 4) { tick(r); tick(r + 2); }
+                        for rr in (r, r + 2):
+                            if rr + 2 < r_end:
+                                hi = max(hi, rr + 3)
+                        r += 4
+                    assert -lead <= lo and hi < ny + lead, (nx, ny, T, nbr, y0, y1, lo, hi)
+
+
 def test_sweep_plan_rejects_bad_arguments(csim):
     for args in ((0, 5, 3), (5, 0, 3), (5, 5, 0), (5, 5, 5)):
         with pytest.raises(csim.CsimError):

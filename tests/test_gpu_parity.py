@@ -389,7 +389,7 @@ def test_minmax_and_health(csim, ctx):
 
 # ---- multi-GPU halo exchange (needs >= 2 devices; the 1-GPU box skips) ---------------------------
 
-def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors, p2p=False):
+def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors):
     try:
         c = csim.Context(rank)
         c.comm_init(size, rank, uid)
@@ -398,8 +398,6 @@ def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, result
         u = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         tmp = csim.Field(c, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
         u.upload(t0)
-        if p2p:
-            csim.peer_setup(u, tmp, dec)
         p = csim.make_step_params(*phys, csim.BCConfig(*[csim.BCType(b) for b in bc]), dec, 0.0, flags)
         for k in steps:  # several calls: the block structure must not leak across calls
             csim.run_steps(u, tmp, p, dec, k)
@@ -409,12 +407,12 @@ def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, result
         errors.append((rank, repr(e)))
 
 
-def _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=0, p2p=False):
+def _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=0):
     import threading
     uid = csim.comm_unique_id()
     results, errors = {}, []
     th = [threading.Thread(target=_rank_worker, args=(csim, size, r, uid, nxg, nyg, steps, phys, bc, flags,
-                                                      results, errors, p2p)) for r in range(size)]
+                                                      results, errors)) for r in range(size)]
     [t.start() for t in th]
     [t.join(180) for t in th]
     assert not errors, errors
@@ -446,8 +444,6 @@ def test_multi_gpu_matches_single_rank_oracle(csim, oracle_mod, port):
             want = port.run(sp)["final"]
             got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc)
             assert bits_equal(got, want), ("blocked, NCCL exchange", size, nxg, nyg)
-            got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, p2p=True)
-            assert bits_equal(got, want), ("blocked, peer-memory push", size, nxg, nyg)
             got = _run_ranks(csim, size, nxg, nyg, steps, phys, bc, flags=csim.STEP_NO_TEMPORAL)
             assert bits_equal(got, want), ("one-line", size, nxg, nyg)
 
@@ -466,9 +462,9 @@ def test_cpp_dropin_unit_tests():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
 
 
-def test_multi_process_parity_over_ipc_and_nccl():
-    """One PROCESS per GPU under torchrun (how bench.py runs): the peer-memory path maps the
-    neighbours' tiles with CUDA IPC here, which the threaded test above cannot exercise."""
+def test_multi_process_parity_under_torchrun():
+    """One PROCESS per GPU under torchrun (how bench.py runs), with the CUDA-graph replay of the block
+    loop on and off."""
     import os
     import subprocess
     import sys
