@@ -6,17 +6,23 @@
         --master-port P bench.py --gpus N --steps K --warmup W   # one rank per GPU
     python bench.py --impl reference ...                          # the reference's CPU code
 
-Workload (BASELINE.json configs[1]; per-GPU tile fixed as N grows → weak scaling): an 8192x8192
-tile per GPU, Gaussian hotspot, dx=dy=1, D=0.05, vx=0.5, vy=0, dt=0.1, all-periodic boundaries
-(= frozen zero ghosts), 2-D Cartesian decomposition {1,1},{2,1},{2,2},{4,2}.
-`--tile 16384` gives configs[2].
+Workload (BASELINE.json configs[2], the tile north_star's target is stated on; per-GPU tile fixed as N
+grows → weak scaling): a 16384x16384 tile per GPU, Gaussian hotspot, dx=dy=1, D=0.05, vx=0.5, vy=0,
+dt=0.1, all-periodic boundaries (= frozen zero ghosts), 2-D Cartesian decomposition
+{1,1},{2,1},{2,2},{4,2}.  `--tile 8192` gives configs[1].
 
 A bench "step" is one output window of `--inner` (default 100, dev.yaml's out_every) time steps:
   value : cells * inner * K / device time, fields resident in HBM, timed with CUDA events on the
           library's stream, max over ranks.
-  e2e   : same window through the C ABI with HOST buffers: H2D of the padded tile from pinned
-          memory, `inner` steps, D2H of the de-haloed tile (what the reference hands to its NetCDF
-          writer at an output step), every step, inside the timed region.
+  e2e   : ONE simulation through the C ABI with HOST buffers, as the reference's main() runs it
+          (src/main.cpp:71,93-109): the initial tile goes up from pinned memory once, then every window
+          is `inner` time steps followed by the device→host copy of the de-haloed tile (what
+          write_field_netcdf hands to the file layer), the copy of window k overlapping the steps of
+          window k+1.  The upload and every download are inside the timed region.
+  parity: after the timing, K time steps from the initial condition are run again and >= 8 windows of
+          every rank's tile (rank seams, tile corners, physical edges, deep interior) are compared bit for
+          bit with the CPU oracle run on the sub-domain around each window; for the headline physics
+          and for the all-terms physics.  A mismatch exits non-zero.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -32,8 +38,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PHYS = dict(D=0.05, vx=0.5, vy=0.0, dt=0.1)  # configs/dev.yaml physics
-ALG_BYTES_PER_CELL = 16.0                     # one 8-byte read + one 8-byte write per cell update
+PHYS = dict(D=0.05, vx=0.5, vy=0.0, dt=0.1)          # configs/dev.yaml physics
+PHYS_ALL_TERMS = dict(D=0.05, vx=-0.5, vy=0.25, dt=0.1)  # both velocity components, forward difference in x
+ALG_BYTES_PER_CELL = 16.0                              # one 8-byte read + one 8-byte write per cell update
+NVLINK_GBS_PER_DIRECTION = 900.0                       # NVLink 5, per GPU and direction (B200_PROFILING.md)
 METRIC = "cell updates/sec (diffusion+advection step)"
 
 
@@ -114,6 +122,13 @@ def workload_name(tile, dims):
             f"decomp {{{dims[0]},{dims[1]}}} (global {tile * dims[0]}x{tile * dims[1]})")
 
 
+def base_config(args, dims, inner):
+    """The `config` keys both arms print (the reference arm differs only in timesteps_per_step)."""
+    return {"workload": workload_name(args.tile, dims), "timesteps_per_step": inner,
+            "parallelism": f"cartesian {dims[0]}x{dims[1]}, 1 rank per GPU", "physics": dict(PHYS),
+            "tile": args.tile, "bc": args.bc}
+
+
 # -------------------------------------------------------------------------------------------------
 def cpu_reference_rate(tile, timesteps, threads):
     """The reference's own compute objects (oracle/_ref) on `threads` emulated ranks: returns
@@ -165,14 +180,17 @@ def run_reference(args):
                         "sample": f"1 time step of the {tile}x{tile} tile, flagless build (-O0) of the reference objects"}
     except Exception:  # noqa: BLE001
         flagless = None
-    sample = (f"bounded sample: ONE {tile}x{tile} tile (the per-GPU tile of the workload) split over {used} "
-              f"emulated ranks (threads), {inner} time steps per bench step, loop time only (main.cpp:89-123 timing region without NetCDF writes); "
-              f"reference compute objects, -O2, no MPI launcher (MPI not installed)")
+    sample = (f"bounded sample: ONE {tile}x{tile} tile (the per-GPU tile of the workload, whatever --gpus says: the "
+              f"CPU arm does not grow with N) split over {used} emulated ranks (threads), {inner} time steps per "
+              f"bench step, loop time only (main.cpp:89-123 timing region without NetCDF writes); reference compute "
+              f"objects, -O2, no MPI launcher (MPI not installed)")
+    cfg = base_config(args, dims_for(args.gpus), inner)
+    cfg["workload"] += "; reference arm: ONE tile on the host cores"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(tile, dims_for(args.gpus)), "timesteps_per_step": inner},
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": used, "kind": kind, "sample": sample,
                          "flagless_build": flagless},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,6 +201,45 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------------
+def parity_windows(dec, w):
+    """Top-left corners (local y, x) of the checked windows of one rank's tile: the four tile corners (a
+    rank seam crossing, a four-corner point of the decomposition or a corner of the physical domain, depending
+    on where the rank sits), the four edge midpoints, the centre and two off-centre interior points."""
+    nx, ny = dec.nx_local, dec.ny_local
+    w = min(w, nx, ny)
+    pts = [(0, 0), (0, nx - w), (ny - w, 0), (ny - w, nx - w),
+           (0, (nx - w) // 2), (ny - w, (nx - w) // 2), ((ny - w) // 2, 0), ((ny - w) // 2, nx - w),
+           ((ny - w) // 2, (nx - w) // 2), (min(1234, ny - w), min(4321, nx - w)), (min(ny - w, 3 * ny // 4), nx // 3)]
+    return sorted(set(pts)), w
+
+
+def check_parity(csim, co, port, got, dec, nxg, nyg, phys, bc_codes, steps, w=64):
+    """Bit-compare windows of `got` (this rank's interior after `steps` time steps from the initial condition)
+    with the CPU oracle advanced on the sub-domain around each window.  The sub-domain reaches `steps` cells
+    beyond the window (the dependency cone of `steps` 5-point updates) or to the physical boundary; its cut
+    sides carry the neighbouring cells' initial values as frozen ghosts, whose error cannot reach the window
+    in `steps` steps.  Returns (windows checked, windows that differ)."""
+    pts, w = parity_windows(dec, w)
+    bad = 0
+    for (y, x) in pts:
+        gy, gx = dec.y_offset + y, dec.x_offset + x
+        y0, y1 = max(gy - steps, 0), min(gy + w + steps, nyg)
+        x0, x1 = max(gx - steps, 0), min(gx + w + steps, nxg)
+        sub = np.zeros((y1 - y0 + 2, x1 - x0 + 2))  # padded; ghosts outside the physical domain stay 0
+        iy0, iy1, ix0, ix1 = max(y0 - 1, 0), min(y1 + 1, nyg), max(x0 - 1, 0), min(x1 + 1, nxg)
+        ic = csim.initial_condition_host(csim.Decomp2D.window(nxg, nyg, ix0, iy0, ix1 - ix0, iy1 - iy0), 0, 1.0, 1.0)
+        sub[iy0 - (y0 - 1):iy1 - (y0 - 1), ix0 - (x0 - 1):ix1 - (x0 - 1)] = ic
+        bc = (bc_codes[0] if x0 == 0 else 2, bc_codes[1] if x1 == nxg else 2,
+              bc_codes[2] if y0 == 0 else 2, bc_codes[3] if y1 == nyg else 2)
+        sp = co.SimParams(nx=x1 - x0, ny=y1 - y0, steps=steps, out_every=steps, bc=bc, **phys)
+        want = port.run(sp, u0_padded=sub)["final"]
+        a = np.ascontiguousarray(got[y:y + w, x:x + w])
+        b = np.ascontiguousarray(want[gy - y0:gy - y0 + w, gx - x0:gx - x0 + w])
+        if not np.array_equal(a.view(np.uint64), b.view(np.uint64)):
+            bad += 1
+    return len(pts), bad
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -201,6 +258,7 @@ def run_ours(args):
 
     csim = importlib.import_module("climate-sim-mpi-cpp_b200")
     ctx = csim.Context(local_rank)
+    numa_node = ctx.bind_numa()  # pinned buffers below are first touched on the GPU's own NUMA node
     tile, inner = args.tile, args.inner
     dims = csim.Decomp2D.init(world, 0, 1, 1).dims
     nxg, nyg = tile * dims[0], tile * dims[1]
@@ -221,19 +279,14 @@ def run_ours(args):
     host_in = ctx.pinned_empty((dec.ny_local + 2, dec.nx_local + 2))
     host_in[:] = 0.0
     csim.initial_condition_host(dec, 1, 1.0, 1.0, out=host_in)
-    host_out = ctx.pinned_empty((dec.ny_local, dec.nx_local))
+    host_out = [ctx.pinned_empty((dec.ny_local, dec.nx_local)) for _ in range(2)]
     u = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
     tmp = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
     u.upload(host_in)
     halo_path = "none"
     if world > 1:
-        # default: T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block over NVLink,
-        # hidden behind the interior sweep.  CSIM_HALO=p2p selects the peer-memory push instead, which
-        # measured slower with the round-1b kernel (profiles/r01b_weak_scaling.md).
-        halo_path = "pack + grouped NCCL send/recv over NVLink + unpack, overlapped with the interior sweep"
-        if os.environ.get("CSIM_HALO", "nccl") == "p2p":
-            csim.peer_setup(u, tmp, dec)  # neighbours' tiles mapped over CUDA IPC: direct NVLink stores
-            halo_path = "peer-memory push (CUDA IPC over NVLink) + flag, NCCL only for bootstrap"
+        halo_path = ("T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block over NVLink, unpack "
+                     "kernel; hidden behind the interior sweep; the block loop replayed as a CUDA graph")
 
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
@@ -242,6 +295,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum_int(v):
+        if world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -258,14 +325,7 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count - l0
         barrier()
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-            launches = int(lt.item())
-        return ms, launches
+        return reduce_max(ms), reduce_sum_int(launches)
 
     enqueue_s = []
 
@@ -274,12 +334,6 @@ def run_ours(args):
         csim.run_steps(u, tmp, params, dec, inner)
         enqueue_s.append(time.perf_counter() - t0)  # host time to enqueue one window (no sync inside)
 
-    def window_e2e():
-        u.upload_async(host_in)
-        csim.run_steps(u, tmp, params, dec, inner)
-        u.download_interior_async(host_out)
-        ctx.sync()  # the caller needs the frame on the host before the next window
-
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, launches = timed(window_resident, args.steps, args.warmup)
@@ -287,77 +341,95 @@ def run_ours(args):
     # dev.yaml has vy = 0, so on the (clean, monotone) benchmark field the library drops the y-advection
     # term: 11 instead of 14 FP64 operations per cell (csim_field_value_state).  Time the same window
     # with both velocity components non-zero and negative vx as well, so the full arithmetic and the
-    # forward-difference branches are on record next to the headline.
+    # forward-difference branches are on record next to the headline, with the same number of windows.
     dropped = u.value_state == 1 and (PHYS["vx"] == 0.0 or PHYS["vy"] == 0.0) and csim.steps_per_sweep() >= 3
-    gen_params = csim.make_step_params(PHYS["D"], -0.5, 0.25, PHYS["dt"], bcs, dec)
+    gen_params = csim.make_step_params(*[PHYS_ALL_TERMS[k] for k in ("D", "vx", "vy", "dt")], bcs, dec)
 
     def window_general():
         csim.run_steps(u, tmp, gen_params, dec, inner)
 
-    gen_steps = max(2, min(args.steps, 5))
-    ms_gen, _ = timed(window_general, gen_steps, 1)
-    e2e_steps = max(2, min(args.steps, 3))
-    ms_e2e = None
+    gen_steps = args.steps
+    sampler_g = ClockSampler(local_rank)
+    sampler_g.start()
+    ms_gen, _ = timed(window_general, gen_steps, 2)
+    clocks_gen = sampler_g.stop()
+
+    # ---- halo timeline (N > 1): one window run eagerly with timestamps around every exchange -------------
+    halo = None
+    if world > 1:
+        barrier()
+        csim.halo_profile(ctx, True)
+        csim.run_steps(u, tmp, params, dec, inner)
+        st = csim.halo_stats(ctx)
+        barrier()
+        wire = st["bytes_per_exchange"]
+        us_max = reduce_max(st["exchange_us"])
+        halo = {
+            "bytes_sent_per_exchange_per_gpu": reduce_max(float(wire)),
+            "formula": "8 B x sum over the up to 8 neighbours of (T lines x band length | T x T corner), T = "
+                       f"{csim.steps_per_sweep()} (SURVEY.md 8d: 8*(edges_x*ny + edges_y*(nx+2))*T plus corners)",
+            "exchanges_per_window": st["blocks"],
+            "us_per_exchange": us_max,
+            "us_first_exchange": reduce_max(st["first_exchange_us"]),
+            "achieved_gbs_per_direction": (wire / (us_max * 1e-6) / 1e9) if us_max > 0 else None,
+            "nvlink_peak_gbs_per_direction": NVLINK_GBS_PER_DIRECTION,
+            "frac_of_nvlink": (wire / (us_max * 1e-6) / 1e9 / NVLINK_GBS_PER_DIRECTION) if us_max > 0 else None,
+            "overlap_fraction": -reduce_max(-st["overlap_fraction"]),  # the worst rank
+            "us_frame_sweep": reduce_max(st["frame_us"]), "us_interior_sweep": reduce_max(st["interior_us"]),
+            "note": "pack kernel + grouped NCCL send/recv + unpack kernel, CUDA events on the exchange stream, one "
+                    "eager (un-graphed) window; max over ranks; overlap_fraction = share of the exchange time that "
+                    "lies inside the concurrently running interior sweep (latency-bound: a 393 KB band is 0.4 us of "
+                    "wire time at 900 GB/s)",
+        }
+
+    # ---- end to end: one simulation with host buffers ---------------------------------------------------
+    e2e = None
     if not args.no_e2e:
-        ms_e2e, _ = timed(window_e2e, e2e_steps, 1)
+        e2e_steps = max(3, min(args.steps, 6))
 
-    # The same end-to-end window with THREE windows in flight (one GPU only): extra contexts with their
-    # own stream, tiles and pinned buffers, so that one window's PCIe copies (H2D before, D2H after its
-    # 100 steps) overlap the other window's sweeps.  Every window still pays its own H2D and D2H inside
-    # the timed region; only the overlap is new.  This is the throughput a caller with independent
-    # members to advance (an ensemble) gets from the same C-ABI calls.
-    ms_pipe, pipe_steps, n_lanes = None, 0, 3
-    if world == 1 and not args.no_e2e:
-        lanes = [(ctx, u, tmp, host_in, host_out)]
-        for _ in range(n_lanes - 1):
-            c2 = csim.Context(local_rank)
-            hin2 = c2.pinned_empty(host_in.shape)
-            hin2[:] = host_in
-            lanes.append((c2, csim.Field(c2, dec.nx_local, dec.ny_local, 1, 1.0, 1.0),
-                          csim.Field(c2, dec.nx_local, dec.ny_local, 1, 1.0, 1.0), hin2,
-                          c2.pinned_empty(host_out.shape)))
-        per_lane = max(2, min(args.steps, 4))
-        pipe_steps = n_lanes * per_lane
-        errors = []
+        def simulation(nwin):
+            pending = [None, None]
+            u.upload_async(host_in)  # H2D of the padded initial tile from pinned memory (main.cpp:71)
+            for k in range(nwin):
+                csim.run_steps(u, tmp, params, dec, inner)
+                if pending[k % 2] is not None:
+                    ctx.event_wait(pending[k % 2])  # the host buffer is free again (its frame was consumed)
+                pending[k % 2] = u.snapshot_async(host_out[k % 2])  # D2H of the de-haloed tile (io.cpp:411-418)
+            for ev in pending:
+                if ev is not None:
+                    ctx.event_wait(ev)
+            ctx.sync()
 
-        def lane_loop(lane, count):
-            # one host thread per lane: a lane blocks in its own context (value scan after the upload,
-            # final sync) without holding up the others; ctypes releases the GIL during the calls
-            c, uu, tt, hin, hout = lane
-            try:
-                for _ in range(count):
-                    uu.upload_async(hin)
-                    csim.run_steps(uu, tt, params, dec, inner)
-                    uu.download_interior_async(hout)
-                    c.sync()  # the frame is on the host
-            except Exception as exc:  # noqa: BLE001
-                errors.append(exc)
-
-        def run_lanes(count):
-            ths = [threading.Thread(target=lane_loop, args=(lane, count)) for lane in lanes]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-            if errors:
-                raise errors[0]
-
-        run_lanes(1)
-        torch.cuda.synchronize()
+        simulation(2)  # warm-up: staging buffers, graph capture
+        barrier()
         t0 = time.perf_counter()
-        run_lanes(per_lane)
-        torch.cuda.synchronize()
-        ms_pipe = 1e3 * (time.perf_counter() - t0)  # several streams: wall clock around a full drain
-        for lane in lanes[1:]:
-            if not np.array_equal(host_out, lane[4]):
-                raise SystemExit("bench.py: the pipelined lanes disagree")
-            lane[1].close()
-            lane[2].close()
-            lane[0].close()
+        simulation(e2e_steps)
+        secs = time.perf_counter() - t0
+        barrier()
+        secs = reduce_max(secs)
+        # strict per-window variant: every window pays its own H2D and D2H, one after the other
+        def window_copies():
+            u.upload_async(host_in)
+            csim.run_steps(u, tmp, params, dec, inner)
+            u.download_interior_async(host_out[0])
+            ctx.sync()
+
+        ms_serial, _ = timed(window_copies, 2, 1)
+        cells_w = float(nxg) * float(nyg) * inner
+        e2e = {"value": cells_w * e2e_steps / secs, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": int(host_in.nbytes // e2e_steps), "d2h_bytes_per_step": int(host_out[0].nbytes),
+               "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
+               "mode": "ONE simulation per rank through the C ABI with pinned host buffers: H2D of the initial tile "
+                       f"({host_in.nbytes} B, once, inside the timed region, amortised over the windows in "
+                       "h2d_bytes_per_step), then per window 100 time steps + D2H of the de-haloed tile on the copy "
+                       "stream, overlapping the next window's steps (what src/main.cpp:93-99 does at output steps); "
+                       "host wall clock around a full drain, max over ranks",
+               "per_window_copies": {"value": cells_w * 2 / (ms_serial * 1e-3), "ms_per_step": ms_serial / 2,
+                                     "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out[0].nbytes),
+                                     "mode": "every window: H2D of the padded tile, 100 steps, D2H, sync — no overlap"}}
 
     cells_per_window = float(nxg) * float(nyg) * inner
     value = cells_per_window * args.steps / (ms * 1e-3)
-    e2e_value = cells_per_window * e2e_steps / (ms_e2e * 1e-3) if ms_e2e else None
     gen_value = cells_per_window * gen_steps / (ms_gen * 1e-3)
 
     # sanity: the field must still be finite and must have moved (the work was really done)
@@ -365,7 +437,40 @@ def run_ours(args):
     if bad or not (0.0 < max_abs <= 1.0):
         raise SystemExit(f"bench.py: field unhealthy after timing (max|u|={max_abs}, nonfinite={bad})")
 
-    # roofline of the dominant kernel: the fused sweep k_step_tb, which advances T steps per launch.
+    # ---- parity, outside every timed region ---------------------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        from oracle import cpu_oracle as co  # the checker, never the thing measured
+        if not co.available("port"):
+            co.build()
+        port = co.Oracle("port")
+        T = csim.steps_per_sweep()
+        K = max(args.parity_steps, 2 * T + 1)  # at least two blocks and a remainder sweep
+        n_win = n_bad = 0
+        sets = []
+        for name, phys in (("headline", PHYS), ("all_terms", PHYS_ALL_TERMS)):
+            u.upload(host_in)
+            pp = csim.make_step_params(phys["D"], phys["vx"], phys["vy"], phys["dt"], bcs, dec)
+            csim.run_steps(u, tmp, pp, dec, K)
+            u.download_interior_async(host_out[0])
+            ctx.sync()
+            w, b = check_parity(csim, co, port, host_out[0], dec, nxg, nyg, phys, bcs.as_tuple(), K)
+            n_win += w
+            n_bad += b
+            sets.append(name)
+        n_win, n_bad = reduce_sum_int(n_win), reduce_sum_int(n_bad)
+        parity = {"windows": n_win, "steps": K, "bit_identical": n_bad == 0, "windows_differing": n_bad,
+                  "window": "64x64 cells", "per_rank": n_win // world, "parameter_sets": sets,
+                  "against": "CPU oracle (oracle/oracle_port.c, pinned to the reference's objects by tests/test_oracle.py) "
+                             "advanced on the sub-domain around each window: tile corners (rank seams / decomposition "
+                             "corners / physical corners), edge midpoints, interior"}
+        if n_bad:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "parity": parity, "error": "GPU field differs from the oracle"}),
+                      flush=True)
+            raise SystemExit(3)
+
+    # ---- roofline of the dominant kernel: the fused sweep k_step_tb, which advances T steps per launch ----
     # With all-periodic boundaries no boundary kernels run, so on one GPU the timed region is exactly
     # the sweeps; with N>1 the pack/NCCL/unpack and frame launches share the region (sweep count is
     # computed, not taken from the launch counter).
@@ -377,65 +482,62 @@ def run_ours(args):
     steps_per_launch = inner / sweeps_per_window
     bytes_per_launch = float(dec.nx_local) * float(dec.ny_local) * ALG_BYTES_PER_CELL * steps_per_launch
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{tile}_T{T}", {}).get("bytes_per_launch")
+            ent = json.load(open(tpath)).get(f"{dec.nx_local}x{dec.ny_local}_T{T}", {})
+            traffic = ent.get("bytes_per_launch")
+            traffic_src = ent.get("source")
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"csim::k_step_tb<T={T}> (fused diffusion+advection sweep, {T} steps per launch"
-                                              + (", y-advection term dropped: vy == +0.0)" if dropped else ")"),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": f"csim::k_step_tb<T={T}> (fused diffusion+advection sweep, {T} steps per launch"
+                          + (", y-advection term dropped: vy == +0.0)" if dropped else ")"),
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": launch_ms,
                 "steps_per_launch": steps_per_launch, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "dram_frac_of_peak": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "note": "algorithmic bytes = 16 B per cell update; temporal blocking moves 16/T B per update "
-                        "through HBM, so frac > 1 is expected; measured DRAM traffic per launch is in `traffic`; at "
-                        "T = 3 the kernel runs the FP64 pipe at ~74 % and HBM at ~79 % of the measured peak "
-                        "(DESIGN.md 4.1)"}
+                        "through HBM, so frac > 1 is expected; `traffic` = dram__bytes_read+write per launch of this "
+                        "kernel on this tile from the committed ncu capture named in traffic_source (a one-GPU figure: "
+                        "counters cannot be read outside a profiler); dram_frac_of_peak = traffic / live launch time / peak"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 64)
-        ref_steps = args.ref_inner * 20  # ≈ 10 s of CPU work at 8192² on 16 threads
+        ref_steps = max(4, int(args.ref_inner * 20 * (8192.0 / tile) ** 2))  # ≈ 10-20 s of CPU work
         rate, secs, kind, used = cpu_reference_rate(tile, ref_steps, threads)
         cpu = {"value": rate, "unit": "cell-updates/s", "cores": used, "kind": kind,
                "sample": f"{tile}x{tile}, {ref_steps} time steps of the same workload on {used} emulated ranks "
                          f"(threads), {secs:.1f} s loop time; reference compute objects -O2, no MPI launcher"}
 
     if rank == 0:
+        cfg = base_config(args, dims, inner)
+        if args.global_size:
+            cfg["workload"] = (f"{nxg}x{nyg} global (strong scaling), Gaussian hotspot, diffusion+advection, BCs left/bottom "
+                               f"Dirichlet, right/top Neumann, decomp {{{dims[0]},{dims[1]}}}, tile {dec.nx_local}x{dec.ny_local}"
+                               if args.bc == "dn" else
+                               f"{nxg}x{nyg} global (strong scaling), periodic BCs, decomp {{{dims[0]},{dims[1]}}}")
+        cfg.update({
+            "halo_exchange": halo_path,
+            "arithmetic": ("vy == +0.0 on a scanned-clean field: y-advection term dropped, 11 FP64 ops per "
+                           "cell, bit-identical (DESIGN.md 4.1)") if dropped else "full, 14 FP64 ops per cell",
+            "l2_policy": f"inputs larger than L2 (two {host_in.nbytes >> 20} MiB fields per GPU vs 126 MB L2); no flush needed"
+            if tile >= 4096 else "WARNING: fields fit in L2",
+            "e2e_workload": "one simulation per rank: upload once, a de-haloed frame to the host every 100 steps",
+            "numa_node_of_pinned_buffers": numa_node})
         line = {
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.global_size else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(tile, dims) if not args.global_size else
-                       (f"{nxg}x{nyg} global (strong scaling), Gaussian hotspot, diffusion+advection, BCs left/bottom "
-                        f"Dirichlet, right/top Neumann, decomp {{{dims[0]},{dims[1]}}}, tile {dec.nx_local}x{dec.ny_local}"
-                        if args.bc == "dn" else f"{nxg}x{nyg} global (strong scaling), periodic BCs, decomp {{{dims[0]},{dims[1]}}}"),
-                       "timesteps_per_step": inner,
-                       "parallelism": f"cartesian {dims[0]}x{dims[1]}, 1 rank per GPU", "halo_exchange": halo_path,
-                       "physics": dict(PHYS),
-                       "arithmetic": ("vy == +0.0 on a scanned-clean field: y-advection term dropped, 11 FP64 ops per "
-                                      "cell, bit-identical (DESIGN.md 4.1)") if dropped else "full, 14 FP64 ops per cell",
-                       "l2_policy": "inputs larger than L2 (two 537 MB fields per GPU vs 126 MB L2); no flush needed"
-                       if tile >= 4096 else "WARNING: fields fit in L2"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": ({"value": cells_per_window * pipe_steps / (ms_pipe * 1e-3), "unit": "cell-updates/s",
-                     "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
-                     "steps": pipe_steps, "ms_per_step": ms_pipe / pipe_steps,
-                     "mode": f"{n_lanes} windows in flight (one context each on the GPU): every window's H2D and D2H are "
-                             "inside the timed region and overlap the other windows' sweeps; one host thread per window "
-                             "lane; host wall clock around a full drain",
-                     "serial": {"value": e2e_value, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                                "mode": "one window at a time: H2D, 100 steps, D2H, sync"}}
-                    if ms_pipe else None if ms_e2e is None else
-                    {"value": e2e_value, "unit": "cell-updates/s",
-                     "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out.nbytes),
-                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                     "mode": "one window at a time per rank: H2D, 100 steps, D2H, sync"}),
-            "all_terms": {"value": gen_value, "unit": "cell-updates/s", "vx": -0.5, "vy": 0.25, "steps": gen_steps,
-                          "note": "same window with both velocity components non-zero (14 FP64 ops per cell)"},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "halo": halo,
+            "all_terms": {"value": gen_value, "unit": "cell-updates/s", "vx": PHYS_ALL_TERMS["vx"],
+                          "vy": PHYS_ALL_TERMS["vy"], "steps": gen_steps, "ms_per_step": ms_gen / gen_steps,
+                          "clocks": clocks_gen,
+                          "note": "same windows with both velocity components non-zero (14 FP64 ops per cell): the "
+                                  "rate of a run whose velocity has no exact zero component"},
             "gpu_launches": launches, "clocks": clocks,
             "host_enqueue_ms_per_step": 1e3 * float(np.median(enqueue_s[-args.steps:])) if enqueue_s else None,
         }
@@ -454,11 +556,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--tile", type=int, default=8192, help="per-GPU tile edge (8192 = configs[1], 16384 = configs[2])")
+    ap.add_argument("--tile", type=int, default=16384, help="per-GPU tile edge (16384 = configs[2], 8192 = configs[1])")
     ap.add_argument("--inner", type=int, default=100, help="time steps per bench step (output window)")
-    ap.add_argument("--ref-inner", type=int, default=4, help="time steps per bench step for the CPU reference")
+    ap.add_argument("--ref-inner", type=int, default=1, help="time steps per bench step for the CPU reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end windows (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end simulation (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bit-parity windows (profiling runs)")
+    ap.add_argument("--parity-steps", type=int, default=10, help="time steps of the parity run (>= 2T+1)")
     ap.add_argument("--global-size", type=int, default=0,
                     help="strong scaling: fixed NxN global grid split over the ranks (32768 = configs[3])")
     ap.add_argument("--bc", choices=["periodic", "dn"], default="periodic",

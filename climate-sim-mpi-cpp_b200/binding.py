@@ -71,6 +71,13 @@ class _FieldInfo(C.Structure):
                 ("rows", C.c_int64), ("base", C.c_void_p), ("interior", C.c_void_p)]
 
 
+class HaloStats(C.Structure):
+    """csim_halo_stats"""
+    _fields_ = [("blocks", C.c_int), ("bytes_per_exchange", C.c_size_t), ("first_exchange_us", C.c_double),
+                ("exchange_us", C.c_double), ("overlap_fraction", C.c_double), ("frame_us", C.c_double),
+                ("interior_us", C.c_double), ("total_ms", C.c_double)]
+
+
 class StepParams(C.Structure):
     """csim_step_params"""
     _fields_ = [("D", C.c_double), ("vx", C.c_double), ("vy", C.c_double), ("dt", C.c_double),
@@ -150,9 +157,19 @@ def lib():
             "csim_initial_condition_host": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int,
                                             C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                             C.c_double, C.c_double],
+            "csim_initial_condition_device": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int, C.c_double,
+                                              C.c_double, C.c_double, C.c_double],
+            "csim_halo_profile": [vp, C.c_int],
+            "csim_field_snapshot_async": [vp, vp, C.c_int, C.POINTER(C.c_void_p)],
+            "csim_bind_thread_to_device_numa": [C.c_int, ip],
+            "csim_halo_stats_get": [vp, C.POINTER(HaloStats)],
         }
         for name, args in sig.items():
-            fn = getattr(L, name)
+            fn = getattr(L, name, None)
+            if fn is None:
+                if os.environ.get("CSIM_LIB_PATH"):  # an older build under A/B timing lacks newer entry points
+                    continue
+                raise ImportError(f"{LIB_PATH} does not export {name}: rebuild it (__graft_entry__.build())")
             fn.argtypes = args
             fn.restype = C.c_int
         L.csim_last_error.restype = C.c_char_p
@@ -165,6 +182,10 @@ def lib():
         L.csim_safe_dt.restype = C.c_double
         L.csim_abi_version.restype = C.c_int
         L.csim_steps_per_sweep.restype = C.c_int
+        if hasattr(L, "csim_exp_variant"):
+            L.csim_exp_variant.restype = C.c_int
+            L.csim_exp_restated.argtypes = [C.c_double, C.c_int]
+            L.csim_exp_restated.restype = C.c_double
         _lib = L
     return _lib
 
@@ -215,6 +236,15 @@ class Context:
         arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
         self._pinned.append(p)
         return arr
+
+    def bind_numa(self) -> int:
+        """Pin the calling thread to the CPUs of this GPU's NUMA node (best effort); returns the node or -1."""
+        node = C.c_int(-1)
+        _check(lib().csim_bind_thread_to_device_numa(self.device, C.byref(node)))
+        return node.value
+
+    def event_wait(self, event):
+        _check(lib().csim_event_wait(self._h, event))
 
     def comm_init(self, size: int, rank: int, unique_id: bytes):
         assert len(unique_id) == UNIQUE_ID_BYTES
@@ -308,6 +338,15 @@ class Field:
     def download_interior_async(self, out: np.ndarray):
         _check(lib().csim_field_download_interior_async(self._h, _ptr(out)))
 
+    def snapshot_async(self, out: np.ndarray, big_endian=False):
+        """De-haloed tile → pinned `out` on the copy stream, overlapped with the time steps queued next;
+        returns the event to pass to Context.event_wait (csim_field_snapshot_async)."""
+        assert out.size == self.nx_local * self.ny_local and out.flags["C_CONTIGUOUS"]
+        ev = C.c_void_p()
+        _check(lib().csim_field_snapshot_async(self._h, out.ctypes.data_as(C.c_void_p), 1 if big_endian else 0,
+                                               C.byref(ev)))
+        return ev
+
     def swap(self, other: "Field"):
         _check(lib().csim_field_swap(self._h, other._h))
 
@@ -366,6 +405,20 @@ class Decomp2D:
     @classmethod
     def single(cls, nx: int, ny: int) -> "Decomp2D":
         return cls.init(1, 0, nx, ny)
+
+    @classmethod
+    def window(cls, nx_global: int, ny_global: int, x_offset: int, y_offset: int, nx_local: int,
+               ny_local: int) -> "Decomp2D":
+        """A tile at an arbitrary position of the global grid, without neighbours (host-side helper: the
+        initial condition of a sub-window, e.g. for window-wise parity checks)."""
+        d = _Decomp()
+        d.dims[0] = d.dims[1] = 1
+        for s in range(4):
+            d.nbr[s] = PROC_NULL
+        d.nx_global, d.ny_global, d.nx_local, d.ny_local = nx_global, ny_global, nx_local, ny_local
+        d.x_offset, d.y_offset = x_offset, y_offset
+        return cls((1, 1), (0, 0), (PROC_NULL, PROC_NULL), (PROC_NULL, PROC_NULL), nx_global, ny_global, nx_local,
+                   ny_local, x_offset, y_offset, d)
 
     @property
     def nbr(self):
@@ -457,3 +510,34 @@ def initial_condition_host(dec: Decomp2D, halo, dx, dy, preset="gaussian_hotspot
                                              dec.ny_global, dx, dy, presets[preset], A, sigma_frac,
                                              xc_frac, yc_frac))
     return out
+
+
+def initial_condition_device(f: "Field", dec: Decomp2D, preset="gaussian_hotspot", A=1.0, sigma_frac=0.05,
+                             xc_frac=0.5, yc_frac=0.5):
+    """src/init.cpp:12-47 generated on the device into the interior of `f` (bit-identical to
+    initial_condition_host when exp_variant() is 0 or 1; raises CsimError(UNSUPPORTED) otherwise)."""
+    presets = {"gaussian_hotspot": 0, "constant_zero": 1}
+    if preset not in presets:
+        raise RuntimeError("Unknown IC preset: " + preset)  # init.cpp:42
+    _check(lib().csim_initial_condition_device(f._h, C.byref(dec._c), dec.nx_global, dec.ny_global,
+                                               presets[preset], A, sigma_frac, xc_frac, yc_frac))
+
+
+def exp_variant() -> int:
+    """Which restated variant of exp() matches the host libm: 1 FMA, 0 plain, -1 neither."""
+    return int(lib().csim_exp_variant())
+
+
+def exp_restated(x: float, variant: int) -> float:
+    return float(lib().csim_exp_restated(x, variant))
+
+
+def halo_profile(ctx: "Context", enable=True):
+    """The next run_steps on a tile with neighbours runs eagerly with timestamps (csim_halo_profile)."""
+    _check(lib().csim_halo_profile(ctx._h, 1 if enable else 0))
+
+
+def halo_stats(ctx: "Context") -> dict:
+    st = HaloStats()
+    _check(lib().csim_halo_stats_get(ctx._h, C.byref(st)))
+    return {name: getattr(st, name) for name, _ in HaloStats._fields_}

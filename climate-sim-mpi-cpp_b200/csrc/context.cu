@@ -101,6 +101,11 @@ int csim_ctx_create(int device, csim_ctx** out) {
     CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming));
+    CSIM_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_snap_packed[b], cudaEventDisableTiming));
+        CSIM_CUDA(cudaEventCreateWithFlags(&c->ev_snap_done[b], cudaEventDisableTiming));
+    }
     c->scratch_doubles = 4096;
     CSIM_CUDA(cudaMalloc(&c->d_scratch, c->scratch_doubles * sizeof(double)));
     CSIM_CUDA(cudaMallocHost(&c->h_scratch, c->scratch_doubles * sizeof(double)));
@@ -136,6 +141,15 @@ int csim_ctx_destroy(csim_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_go) cudaEventDestroy(c->ev_go);
+    if (c->stream_copy) {
+        cudaStreamSynchronize(c->stream_copy);
+        cudaStreamDestroy(c->stream_copy);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (c->ev_snap_packed[b]) cudaEventDestroy(c->ev_snap_packed[b]);
+        if (c->ev_snap_done[b]) cudaEventDestroy(c->ev_snap_done[b]);
+        if (c->d_snapbuf[b]) cudaFree(c->d_snapbuf[b]);
+    }
     if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_wide) cudaFree(c->d_wide);
     if (c->d_snap) cudaFree(c->d_snap);
@@ -149,6 +163,7 @@ int csim_sync(csim_ctx* c) {
     CSIM_CUDA(cudaSetDevice(c->device));
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_copy));
     return CSIM_OK;
 }
 
@@ -337,6 +352,48 @@ int csim_field_download_interior_be_async(const csim_field* f, void* host) {
     CSIM_LAUNCH(c, k_pack_interior_be, grid, block, 0, f->interior(), f->nx, f->ny, f->pitch,
                 reinterpret_cast<unsigned long long*>(c->d_snap));
     CSIM_CUDA(cudaMemcpyAsync(host, c->d_snap, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return CSIM_OK;
+}
+
+int csim_field_snapshot_async(const csim_field* f, void* host, int big_endian, void** event) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr && event != nullptr, CSIM_ERR_INVALID,
+                 "csim_field_snapshot_async: null argument");
+    *event = nullptr;
+    csim_ctx* c = f->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    const size_t n = static_cast<size_t>(f->nx) * static_cast<size_t>(f->ny);
+    const int b = c->snap_next;
+    c->snap_next ^= 1;
+    if (c->snapbuf_doubles[b] < n) {
+        if (c->d_snapbuf[b]) {
+            CSIM_CUDA(cudaStreamSynchronize(c->stream_copy));
+            CSIM_CUDA(cudaFree(c->d_snapbuf[b]));
+            c->d_snapbuf[b] = nullptr;
+            c->snapbuf_doubles[b] = 0;
+        }
+        CSIM_CUDA(cudaMalloc(&c->d_snapbuf[b], (n ? n : 1) * sizeof(double)));
+        c->snapbuf_doubles[b] = n;
+    }
+    if (n) {
+        // the copy that last read this staging buffer must be done before the pack overwrites it
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_snap_done[b], 0));
+        if (big_endian) {
+            const dim3 grid((f->nx + 255) / 256, f->ny < 1024 ? f->ny : 1024);
+            CSIM_LAUNCH(c, k_pack_interior_be, grid, 256, 0, f->interior(), f->nx, f->ny, f->pitch,
+                        reinterpret_cast<unsigned long long*>(c->d_snapbuf[b]));
+        } else {
+            CSIM_LAUNCH(c, k_repitch, repitch_grid(f->nx, f->ny), 256, 0, f->interior(), f->pitch, c->d_snapbuf[b],
+                        f->nx, f->nx, f->ny);
+        }
+        CSIM_CUDA(cudaEventRecord(c->ev_snap_packed[b], c->stream));
+        CSIM_CUDA(cudaStreamWaitEvent(c->stream_copy, c->ev_snap_packed[b], 0));
+        CSIM_CUDA(cudaMemcpyAsync(host, c->d_snapbuf[b], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream_copy));
+        CSIM_CUDA(cudaEventRecord(c->ev_snap_done[b], c->stream_copy));
+    }
+    cudaEvent_t e;
+    CSIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+    CSIM_CUDA(cudaEventRecord(e, n ? c->stream_copy : c->stream));
+    *event = e;
     return CSIM_OK;
 }
 

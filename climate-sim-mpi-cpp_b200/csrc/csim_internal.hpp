@@ -41,6 +41,13 @@ struct csim_ctx {
     size_t stage_doubles = 0;
     double* d_wide = nullptr;  // wide-halo exchange staging: 8 send + 8 recv regions
     size_t wide_doubles = 0;
+    // snapshot hand-off (context.cu, csim_field_snapshot_async): two dense staging buffers, a copy stream
+    cudaStream_t stream_copy = nullptr;
+    double* d_snapbuf[2] = {nullptr, nullptr};
+    size_t snapbuf_doubles[2] = {0, 0};
+    cudaEvent_t ev_snap_packed[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
+    int snap_next = 0;
+    bool exp_table_loaded = false;    // initcond.cu: 2^(k/128) table copied to this device
     void* run_state = nullptr;        // halo.cu: captured block loops (CUDA graphs) and the halo timeline
     cudaStream_t stream_x = nullptr;  // exchange + frame sweep, overlapped with the interior sweep
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_go = nullptr;
@@ -79,6 +86,7 @@ void run_state_destroy(csim_ctx* c);  // halo.cu
 struct StepK;
 enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2 };
 int tb_max_T();
+int tb_max_T_div();
 bool tb_split_pointless(int nchunks, int n_int);
 // kernels.cu
 int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mode);

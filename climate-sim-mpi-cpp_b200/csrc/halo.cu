@@ -515,7 +515,7 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     // Blocking T steps needs T lines from every neighbour and a tile at least T cells wide (every
     // rank's tile: the last rank of a dimension is never the smallest, decomp.cpp:29-30).
     const int min_nx = dec->nx_global / dec->dims[0], min_ny = dec->ny_global / dec->dims[1];
-    int maxT = (mode == MODE_DIV || (p->flags & CSIM_STEP_NO_TEMPORAL)) ? 1 : tb_max_T();
+    int maxT = (p->flags & CSIM_STEP_NO_TEMPORAL) ? 1 : (mode == MODE_DIV ? tb_max_T_div() : tb_max_T());
     if (maxT > min_nx) maxT = min_nx;
     if (maxT > min_ny) maxT = min_ny;
     if (maxT < 1 || (p->flags & CSIM_STEP_NO_TEMPORAL)) {

@@ -1,7 +1,12 @@
 // host_misc.cpp — host-only parts of the path: decomposition, stability limit, initial condition.
 // No device work happens here; these mirror scalar/host logic of the reference.
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <fstream>
+#include <string>
 #include <limits>
 #include <thread>
 #include <vector>
@@ -134,3 +139,56 @@ int csim_initial_condition_host(double* host, const csim_decomp* dec, int halo, 
 }
 
 }  // extern "C"
+
+extern "C" int csim_bind_thread_to_device_numa(int device, int* node) {
+    if (node) *node = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return csim::fail(CSIM_ERR_CUDA, "csim_bind_thread_to_device_numa: bad device index");
+    }
+    std::string id(bus);
+    for (char& ch : id) ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
+    int n = -1;
+    {
+        std::ifstream in("/sys/bus/pci/devices/" + id + "/numa_node");
+        if (!(in >> n)) n = -1;
+    }
+    if (n < 0) return CSIM_OK;  // single-node box or no affinity information
+    std::ifstream in("/sys/devices/system/node/node" + std::to_string(n) + "/cpulist");
+    std::string list;
+    if (!std::getline(in, list) || list.empty()) return CSIM_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    size_t pos = 0;  // "0-31,64-95"
+    while (pos < list.size()) {
+        size_t end = list.find(',', pos);
+        if (end == std::string::npos) end = list.size();
+        const std::string part = list.substr(pos, end - pos);
+        const size_t dash = part.find('-');
+        try {
+            const int lo = std::stoi(part.substr(0, dash));
+            const int hi = dash == std::string::npos ? lo : std::stoi(part.substr(dash + 1));
+            for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; ++cpu) {
+                CPU_SET(cpu, &set);
+                ++count;
+            }
+        } catch (...) {
+            return CSIM_OK;
+        }
+        pos = end + 1;
+    }
+    // keep only CPUs this process may use at all (cgroup / taskset limits)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+        count = 0;
+        for (int cpu = 0; cpu < CPU_SETSIZE; ++cpu) {
+            if (CPU_ISSET(cpu, &set) && !CPU_ISSET(cpu, &allowed)) CPU_CLR(cpu, &set);
+            if (CPU_ISSET(cpu, &set)) ++count;
+        }
+    }
+    if (count == 0) return CSIM_OK;
+    if (sched_setaffinity(0, sizeof set, &set) == 0 && node) *node = n;
+    return CSIM_OK;
+}

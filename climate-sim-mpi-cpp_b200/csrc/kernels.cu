@@ -337,7 +337,10 @@ bool tb_split_pointless(int nchunks, int n_int) { return nchunks < 3 || n_int < 
 int tb_max_T() {
     static int cached = -1;
     if (cached < 0) {
-        cached = 3;  // T = 4 spills registers and measures slower (profiles/r01_tb_tuning.md)
+        // the staged sweep (step_tbs.cuh) runs four levels in the registers the register-only sweep needs
+        // for three; the latter spills at T = 4 and measures slower (profiles/r01_tb_tuning.md)
+        const char* k = std::getenv("CSIM_TB_KERNEL");
+        cached = (k && std::strcmp(k, "reg") == 0) ? 3 : 4;
         if (const char* e = std::getenv("CSIM_TB_MAXT")) {
             const int v = std::atoi(e);
             if (v >= 1 && v <= kTbMaxT) cached = v;
@@ -348,6 +351,16 @@ int tb_max_T() {
 static int tb_env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
+}
+// Blocking depth with IEEE division (non-power-of-two spacing).  The divisions make the sweep
+// compute-bound already at one step per sweep, so blocking in time only adds the re-computed halo
+// cells; measured in profiles/r02_tuning.md.  CSIM_TB_DIV_MAXT = 2 or 3 opts in.
+int tb_max_T_div() {
+    static const int v = [] {
+        const int e = tb_env_int("CSIM_TB_DIV_MAXT", 1);
+        return e >= 1 && e <= 3 ? e : 1;
+    }();
+    return v < tb_max_T() ? v : tb_max_T();
 }
 
 // Advance `u` by T steps into `out` in one sweep.  nbr/bc as in csim_step_params.  Sides with a
@@ -361,6 +374,16 @@ static bool is_pos_zero(double v) {
     return b == 0;
 }
 bool tb_has_zero_variant(int T, int mode) { return (T == 3 || T == 4) && (mode == MODE_UNIT || mode == MODE_RECIP); }
+bool tb_has_staged_variant(int T, int mode) { return (T == 3 || T == 4) && (mode == MODE_UNIT || mode == MODE_RECIP); }
+// CSIM_TB_KERNEL=reg selects the register-only sweep for every depth (A/B timing); default: the staged
+// sweep wherever it exists
+static bool tb_staged_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("CSIM_TB_KERNEL");
+        return !(e && std::strcmp(e, "reg") == 0);
+    }();
+    return on;
+}
 
 // See csim_internal.hpp.  The dropped-term kernels are bit-identical to the full ones when (tb_update)
 //   (1) every cell the sweep reads is finite and no cell is -0.0              → scanned here, once
@@ -408,17 +431,17 @@ int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k,
     return CSIM_OK;
 }
 
-cudaError_t tb_launch(int vxs, int vys, int T, int mode, const TbArgs& a, cudaStream_t stream) {
+cudaError_t tb_launch(int vxs, int vys, bool staged, int T, int mode, const TbArgs& a, cudaStream_t stream) {
     switch ((vxs + 1) * 3 + (vys + 1)) {
-        case 0: return tb_launch_nn(T, mode, a, stream);
-        case 1: return tb_launch_nz(T, mode, a, stream);
-        case 2: return tb_launch_np(T, mode, a, stream);
-        case 3: return tb_launch_zn(T, mode, a, stream);
-        case 4: return tb_launch_zz(T, mode, a, stream);
-        case 5: return tb_launch_zp(T, mode, a, stream);
-        case 6: return tb_launch_pn(T, mode, a, stream);
-        case 7: return tb_launch_pz(T, mode, a, stream);
-        default: return tb_launch_pp(T, mode, a, stream);
+        case 0: return tb_launch_nn(staged, T, mode, a, stream);
+        case 1: return tb_launch_nz(staged, T, mode, a, stream);
+        case 2: return tb_launch_np(staged, T, mode, a, stream);
+        case 3: return tb_launch_zn(staged, T, mode, a, stream);
+        case 4: return tb_launch_zz(staged, T, mode, a, stream);
+        case 5: return tb_launch_zp(staged, T, mode, a, stream);
+        case 6: return tb_launch_pn(staged, T, mode, a, stream);
+        case 7: return tb_launch_pz(staged, T, mode, a, stream);
+        default: return tb_launch_pp(staged, T, mode, a, stream);
     }
 }
 
@@ -567,7 +590,8 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
         if (is_pos_zero(k.vx)) vxs = 0;
         if (is_pos_zero(k.vy)) vys = 0;
     }
-    const cudaError_t e = tb_launch(vxs, vys, T, mode, a, stream);
+    const bool staged = tb_staged_enabled() && tb_has_staged_variant(T, mode);
+    const cudaError_t e = tb_launch(vxs, vys, staged, T, mode, a, stream);
     ++c->launches;
     if (e != cudaSuccess) return cuda_fail(e, "k_step_tb", __FILE__, __LINE__);
     return CSIM_OK;
@@ -682,7 +706,7 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     // IEEE division is compute-bound: blocking in time buys nothing there.  Tiles with neighbours
     // carry one ghost line per csim_halo_exchange, so here they advance one step per sweep
     // (csim_run_steps exchanges T lines and blocks them too).
-    const int maxT = (mode == MODE_DIV || !all_phys) ? 1 : tb_max_T();
+    const int maxT = !all_phys ? 1 : (mode == MODE_DIV ? tb_max_T_div() : tb_max_T());
     // CSIM_DEBUG_SPLIT=1 (measurement aid): run the single-GPU sweep as the interior + frame pair of
     // launches on two streams exactly as the multi-GPU loop does, to price the split by itself.
     static const bool debug_split = tb_env_int("CSIM_DEBUG_SPLIT", 0) != 0;

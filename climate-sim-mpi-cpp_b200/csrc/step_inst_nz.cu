@@ -1,7 +1,7 @@
 // dispatch-target instantiations for upwind selectors vx: -1, vy: 0 (see step_tb_inst.cuh)
 #include "step_tb_inst.cuh"
 namespace csim {
-cudaError_t tb_launch_nz(int T, int mode, const TbArgs& a, cudaStream_t stream) {
-    return tb_launch_signed<-1, 0>(T, mode, a, stream);
+cudaError_t tb_launch_nz(bool staged, int T, int mode, const TbArgs& a, cudaStream_t stream) {
+    return tb_launch_signed<-1, 0>(staged, T, mode, a, stream);
 }
 }  // namespace csim

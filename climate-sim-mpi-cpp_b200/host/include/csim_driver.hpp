@@ -91,6 +91,18 @@ int open_netcdf_parallel(const std::string& filename, const Decomp2D& dec, const
                          int& ncid, int& varid);
 bool write_field_netcdf(int ncid, int varid, const Field& f, const Decomp2D& dec, int step);
 void close_netcdf_parallel(int ncid);
+// Not in the reference: true once a frame of this file could not be written (the writer thread's
+// failures are asynchronous; call after the time loop, before close_netcdf_parallel).  Drains the writer.
+bool netcdf_write_failed(int ncid);
 void write_metadata_netcdf(int ncid, const SimConfig& cfg);
+
+// The file header the writer emits, as bytes (host only, no GPU): dims time(unlimited), y, x and one
+// record variable u(time,y,x) of NC_DOUBLE with global text attributes.  format 5 = CDF-5 (what the
+// reference's NC_CLOBBER|NC_64BIT_DATA creates, src/io.cpp:386); format 2 = CDF-2, the same grammar with
+// 32-bit counts (CSIM_NETCDF_FORMAT=cdf2 makes open_netcdf_parallel write it), which readers without
+// CDF-5 support — scipy.io.netcdf_file — open.  *data_begin receives the offset of record 0.
+std::vector<unsigned char> netcdf_header_bytes(int format, int64_t nx_global, int64_t ny_global, int64_t numrecs,
+                                               const std::vector<std::pair<std::string, std::string>>& attrs,
+                                               int64_t* data_begin);
 
 void apply_initial_condition(const Decomp2D& dec, Field& u, const SimConfig& cfg);

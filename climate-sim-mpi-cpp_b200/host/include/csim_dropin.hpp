@@ -154,3 +154,6 @@ double safe_dt(double dx, double dy, double vx, double vy, double D);
 // driver in host/src/main.cpp calls instead of the five separate statements.
 void run_timesteps(Field& u, Field& tmp, const Decomp2D& dec, const BCConfig& bc, double D, double vx,
                    double vy, double dt, int nsteps);
+// std::min_element / std::max_element over Field::data (src/main.cpp:74-75: the padded tile, ghosts
+// included) as a device reduction: the tile does not travel to the host for two numbers.
+std::pair<double, double> field_minmax(const Field& f);

@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -34,6 +35,13 @@ namespace {
 // ---- big-endian header builder ---------------------------------------------------------------
 struct Bytes {
     std::vector<unsigned char> b;
+    bool wide = true;  // CDF-5: counts, lengths and sizes are 64-bit; CDF-1/2: 32-bit
+    void count(int64_t v) {
+        if (wide)
+            i64(v);
+        else  // a size that does not fit (vsize of a huge record) is written as 2^32-1, as the format says
+            u32(v > 0xFFFFFFFFll - 3 ? 0xFFFFFFFFu : static_cast<uint32_t>(v));
+    }
     void u32(uint32_t v) {
         for (int s = 24; s >= 0; s -= 8) b.push_back(static_cast<unsigned char>(v >> s));
     }
@@ -41,7 +49,7 @@ struct Bytes {
         for (int s = 56; s >= 0; s -= 8) b.push_back(static_cast<unsigned char>(static_cast<uint64_t>(v) >> s));
     }
     void name(const std::string& s) {  // nelems + bytes padded to a multiple of 4
-        i64(static_cast<int64_t>(s.size()));
+        count(static_cast<int64_t>(s.size()));
         b.insert(b.end(), s.begin(), s.end());
         while (b.size() % 4) b.push_back(0);
     }
@@ -62,6 +70,7 @@ struct Cdf5File {
     int nx_global = 0, ny_global = 0;
     int64_t begin = 0, recsize = 0;
     int64_t numrecs = 0;
+    int format = 5;  // 5: CDF-5 (the reference's NC_64BIT_DATA), 2: CDF-2 (CSIM_NETCDF_FORMAT=cdf2)
     std::vector<std::pair<std::string, std::string>> attrs;
     bool header_written = false;
     std::string path;
@@ -88,51 +97,65 @@ Cdf5File* lookup(int ncid) {
     return g_files[static_cast<size_t>(ncid - 1)].get();
 }
 
-std::vector<unsigned char> build_header(const Cdf5File& f, int64_t numrecs, int64_t* begin_out) {
+// The header grammar of the classic NetCDF formats (same for CDF-1, 2 and 5 up to field widths):
+//   magic numrecs dim_list gatt_list var_list
+//   dim_list = NC_DIMENSION nelems [name dim_length]…      (ABSENT = ZERO ZERO)
+//   att      = name nc_type nelems [values, padded to 4]
+//   var      = name ndims [dimid]… vatt_list nc_type vsize begin
+// CDF-5: every count/length/size/dimid is 64-bit; CDF-2: 32-bit, except `begin`, which is 64-bit in both.
+std::vector<unsigned char> header_bytes(int format, int64_t nx_global, int64_t ny_global, int64_t numrecs,
+                                        const std::vector<std::pair<std::string, std::string>>& attrs,
+                                        int64_t* begin_out) {
+    const int64_t recsize = nx_global * ny_global * 8;
     auto emit = [&](int64_t begin) {
         Bytes h;
-        h.b = {'C', 'D', 'F', 5};
-        h.i64(numrecs);
+        h.wide = format == 5;
+        h.b = {'C', 'D', 'F', static_cast<unsigned char>(format)};
+        h.count(numrecs);
         h.u32(NC_DIMENSION);
-        h.i64(3);
+        h.count(3);
         h.name("time");
-        h.i64(0);  // record dimension
+        h.count(0);  // record dimension
         h.name("y");
-        h.i64(f.ny_global);
+        h.count(ny_global);
         h.name("x");
-        h.i64(f.nx_global);
-        if (f.attrs.empty()) {
+        h.count(nx_global);
+        if (attrs.empty()) {
             h.u32(0);
-            h.i64(0);
+            h.count(0);
         } else {
             h.u32(NC_ATTRIBUTE);
-            h.i64(static_cast<int64_t>(f.attrs.size()));
-            for (auto& a : f.attrs) {
+            h.count(static_cast<int64_t>(attrs.size()));
+            for (auto& a : attrs) {
                 h.name(a.first);
                 h.u32(NC_CHAR);
-                h.i64(static_cast<int64_t>(a.second.size()));
+                h.count(static_cast<int64_t>(a.second.size()));
                 h.b.insert(h.b.end(), a.second.begin(), a.second.end());
                 while (h.b.size() % 4) h.b.push_back(0);
             }
         }
         h.u32(NC_VARIABLE);
-        h.i64(1);
+        h.count(1);
         h.name("u");
-        h.i64(3);
-        h.i64(0);
-        h.i64(1);
-        h.i64(2);
+        h.count(3);
+        h.count(0);
+        h.count(1);
+        h.count(2);
         h.u32(0);  // no variable attributes
-        h.i64(0);
+        h.count(0);
         h.u32(NC_DOUBLE);
-        h.i64(f.recsize);  // vsize: one record of u
-        h.i64(begin);
+        h.count(recsize);  // vsize: one record of u
+        h.i64(begin);      // OFFSET: 64-bit in CDF-2 and CDF-5
         return h.b;
     };
     const size_t len = emit(0).size();
     const int64_t begin = (static_cast<int64_t>(len) + kDataAlign - 1) / kDataAlign * kDataAlign;
     if (begin_out) *begin_out = begin;
     return emit(begin);
+}
+
+std::vector<unsigned char> build_header(const Cdf5File& f, int64_t numrecs, int64_t* begin_out) {
+    return header_bytes(f.format, f.nx_global, f.ny_global, numrecs, f.attrs, begin_out);
 }
 
 bool pwrite_all(int fd, const void* p, size_t n, int64_t off) {
@@ -168,7 +191,9 @@ void writer_loop(Cdf5File* f) {
             j = f->jobs.front();
             f->jobs.pop_front();
         }
+        std::string why;
         bool ok = csim_event_wait(csim_host::default_context(), j.event) == CSIM_OK;
+        if (!ok) why = csim_last_error();  // thread-local: only this thread can read it
         if (ok) {
             const char* src = static_cast<const char*>(f->pinned[j.buf]);
             const size_t row = static_cast<size_t>(f->nx) * 8;
@@ -187,7 +212,7 @@ void writer_loop(Cdf5File* f) {
             f->busy[j.buf] = false;
             if (!ok && !f->failed) {
                 f->failed = true;
-                f->error = std::string("Rank write failed: ") + std::strerror(errno);
+                f->error = std::string("Rank write failed: ") + (why.empty() ? std::strerror(errno) : why.c_str());
             }
         }
         f->cv.notify_all();
@@ -197,6 +222,13 @@ void writer_loop(Cdf5File* f) {
 std::string to_s(double v) { return std::to_string(v); }  // "%f", as the reference's std::to_string
 
 }  // namespace
+
+std::vector<unsigned char> netcdf_header_bytes(int format, int64_t nx_global, int64_t ny_global, int64_t numrecs,
+                                               const std::vector<std::pair<std::string, std::string>>& attrs,
+                                               int64_t* data_begin) {
+    if (format != 2 && format != 5) throw std::runtime_error("netcdf_header_bytes: format must be 2 or 5");
+    return header_bytes(format, nx_global, ny_global, numrecs, attrs, data_begin);
+}
 
 void write_metadata_netcdf(int ncid, const SimConfig& cfg) {
     Cdf5File* f = lookup(ncid);
@@ -227,6 +259,12 @@ int open_netcdf_parallel(const std::string& filename, const Decomp2D& dec, const
     f->nx_global = dec.nx_global;
     f->ny_global = dec.ny_global;
     f->recsize = static_cast<int64_t>(dec.nx_global) * dec.ny_global * 8;
+    if (const char* fmt = std::getenv("CSIM_NETCDF_FORMAT")) {
+        if (std::strcmp(fmt, "cdf2") == 0)
+            f->format = 2;
+        else if (std::strcmp(fmt, "cdf5") != 0)
+            throw std::runtime_error(std::string("CSIM_NETCDF_FORMAT must be cdf5 or cdf2, not ") + fmt);
+    }
     f->nx = dec.nx_local;
     f->ny = dec.ny_local;
     f->x_off = dec.x_offset;
@@ -280,9 +318,10 @@ bool write_field_netcdf(int ncid, int /*varid*/, const Field& fld, const Decomp2
         buf = f->busy[0] ? 1 : 0;
         f->busy[buf] = true;
     }
+    // pack + byte swap on the compute stream, the PCIe copy on the copy stream: the steps queued after this
+    // call run while the frame travels
     void* ev = nullptr;
-    const int rc1 = csim_field_download_interior_be_async(fld.data.device_ro(), f->pinned[buf]);
-    const int rc2 = rc1 == CSIM_OK ? csim_event_record(csim_host::default_context(), &ev) : rc1;
+    const int rc2 = csim_field_snapshot_async(fld.data.device_ro(), f->pinned[buf], 1, &ev);
     if (rc2 != CSIM_OK) {
         std::lock_guard<std::mutex> lk(f->mu);
         f->busy[buf] = false;
@@ -298,6 +337,15 @@ bool write_field_netcdf(int ncid, int /*varid*/, const Field& fld, const Decomp2
     return true;
 }
 
+bool netcdf_write_failed(int ncid) {
+    Cdf5File* f = lookup(ncid);
+    if (!f) return true;
+    std::unique_lock<std::mutex> lk(f->mu);
+    f->cv.wait(lk, [&] { return f->jobs.empty() && !f->busy[0] && !f->busy[1]; });
+    if (f->failed) std::cerr << f->error << "\n";
+    return f->failed;
+}
+
 void close_netcdf_parallel(int ncid) {
     Cdf5File* f = lookup(ncid);
     if (!f) return;
@@ -309,12 +357,14 @@ void close_netcdf_parallel(int ncid) {
     f->cv.notify_all();
     if (f->writer.joinable()) f->writer.join();
     // every rank saw the same frame count; rank 0 records it (ncmpi_close flushes numrecs)
-    double n = static_cast<double>(f->numrecs);
-    MPI_Reduce(&n, &n, 1, MPI_DOUBLE, MPI_MAX, 0, MPI_COMM_WORLD);
+    const double n_mine = static_cast<double>(f->numrecs);
+    double n = n_mine;  // separate send and receive buffers: aliasing them needs MPI_IN_PLACE with a real MPI
+    MPI_Reduce(&n_mine, &n, 1, MPI_DOUBLE, MPI_MAX, 0, MPI_COMM_WORLD);
     if (f->owner && f->fd >= 0) {
         f->numrecs = static_cast<int64_t>(n);
         Bytes b;
-        b.i64(f->numrecs);
+        b.wide = f->format == 5;
+        b.count(f->numrecs);
         pwrite_all(f->fd, b.b.data(), b.b.size(), 4);
     }
     if (f->fd >= 0) ::close(f->fd);
@@ -347,6 +397,14 @@ void apply_initial_condition(const Decomp2D& dec, Field& u, const SimConfig& cfg
     c.ny_local = u.ny_local;
     c.x_offset = dec.x_offset;
     c.y_offset = dec.y_offset;
+    // On the device when the host libm's exp() is one the library reproduces bit for bit (no host loop, no
+    // upload); CSIM_IC=host forces the host path.  Needs halo 1 tiles like everything on the fused path.
+    const char* where = std::getenv("CSIM_IC");
+    if (!(where && std::strcmp(where, "host") == 0) && csim_exp_variant() >= 0 && u.dx == cfg.dx && u.dy == cfg.dy) {
+        csim_host::check(csim_initial_condition_device(u.data.device_rw(), &c, cfg.nx, cfg.ny, preset, cfg.ic.A,
+                                                       cfg.ic.sigma_frac, cfg.ic.xc_frac, cfg.ic.yc_frac));
+        return;
+    }
     csim_host::check(csim_initial_condition_host(u.data.data(), &c, u.halo, cfg.nx, cfg.ny, cfg.dx, cfg.dy, preset,
                                                  cfg.ic.A, cfg.ic.sigma_frac, cfg.ic.xc_frac, cfg.ic.yc_frac));
 }

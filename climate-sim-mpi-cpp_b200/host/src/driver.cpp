@@ -60,12 +60,14 @@ struct Driver {
         dec.init(MPI_COMM_WORLD, cfg.nx, cfg.ny);
         Field state(dec.nx_local, dec.ny_local, /*halo=*/1, cfg.dx, cfg.dy);
         Field scratch(dec.nx_local, dec.ny_local, /*halo=*/1, cfg.dx, cfg.dy);
-        apply_initial_condition(dec, state, cfg);  // host libm exp: bit-identical to the reference
+        // generated on the device when the host libm's exp() is one the library can reproduce bit for bit
+        // (csim_exp_variant), on the host otherwise: either way identical to the reference's tile
+        apply_initial_condition(dec, state, cfg);
 
         if (rank == 0) {
-            // main.cpp:73-77: extrema over rank 0's padded tile, ghost cells included
-            const auto mm = std::minmax_element(state.data.begin(), state.data.end());
-            std::cout << "IC min/max: " << *mm.first << " / " << *mm.second << "\n";
+            // main.cpp:73-77: extrema over rank 0's padded tile, ghost cells included (device reduction)
+            const auto mm = field_minmax(state);
+            std::cout << "IC min/max: " << mm.first << " / " << mm.second << "\n";
             std::filesystem::create_directories("outputs");
         }
         MPI_Barrier(MPI_COMM_WORLD);
@@ -76,14 +78,19 @@ struct Driver {
 
         const double t_begin = MPI_Wtime();
         int frame = 0, done = 0;
+        bool failed = false;
         while (done < cfg.steps) {
-            if (done % cfg.out_every == 0) write_field_netcdf(file, var, state, dec, frame++);  // asynchronous
+            if (done % cfg.out_every == 0 && !write_field_netcdf(file, var, state, dec, frame++)) {  // asynchronous
+                failed = true;  // the message is on stderr already (io.cpp:419-421); upstream carries on,
+                break;          // here a lost frame ends the run with a non-zero status
+            }
             const int window = std::min(cfg.out_every - done % cfg.out_every, cfg.steps - done);
             run_timesteps(state, scratch, dec, cfg.bc, cfg.D, cfg.vx, cfg.vy, cfg.dt, window);
             done += window;
         }
         MPI_Barrier(MPI_COMM_WORLD);  // every rank has finished its queued steps
         const double t_steps = MPI_Wtime();
+        failed = netcdf_write_failed(file) || failed;  // a frame the writer thread could not put on disk
         close_netcdf_parallel(file);  // drains the writer thread, patches numrecs
         const double t_end = MPI_Wtime();
 
@@ -94,7 +101,7 @@ struct Driver {
         if (rank == 0)
             std::cout << "timing: total_max=" << worst[0] << " s, worst_avg_step=" << worst[1] << " s\n";
         dec.finalize();
-        return 0;
+        return failed ? 1 : 0;
     }
 };
 

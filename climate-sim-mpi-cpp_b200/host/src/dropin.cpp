@@ -105,10 +105,9 @@ void MirroredData::pull() const {
 }
 void MirroredData::push() const {
     State& s = *st_;
-    if (!s.dev) {
-        check(csim_field_create(default_context(), s.nx, s.ny, s.h, s.dx, s.dy, &s.dev));
-        s.host_newer = true;
-    }
+    // a new tile is zero-filled like the host vector (src/field.cpp:12): nothing to upload unless the
+    // host copy has been handed out for writing (host_rw) or was copy-constructed (both set host_newer)
+    if (!s.dev) check(csim_field_create(default_context(), s.nx, s.ny, s.h, s.dx, s.dy, &s.dev));
     if (s.host_newer) {
         if (!s.host.empty()) check(csim_field_upload(s.dev, s.host.data()));
         s.host_newer = false;
@@ -339,3 +338,9 @@ int MPI_Reduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datat
 }
 
 }  // extern "C"
+
+std::pair<double, double> field_minmax(const Field& f) {
+    double mn = 0.0, mx = 0.0;
+    check(csim_minmax(f.data.device_ro(), &mn, &mx));
+    return {mn, mx};
+}

@@ -237,7 +237,33 @@ static void snapshot_round_trip() {
     std::remove(fname.c_str());
 }
 
+// `test_driver --write-file <path> <2|5> <nx> <ny> <nrec>`: a complete file on the CPU from the writer's own
+// header builder — u[t][y][x] = 1e6 t + 1e3 y + x + 0.25, big-endian — for readers the tests did not write
+// (scipy.io.netcdf_file on the CDF-2 flavour, tests/test_driver.py).
+static int write_file(const std::string& path, int format, int nx, int ny, int nrec) {
+    const std::vector<std::pair<std::string, std::string>> attrs = {
+        {"description", "climate-sim-mpi-cpp"}, {"grid", std::to_string(nx) + " x " + std::to_string(ny)},
+        {"dt", std::to_string(0.1)}, {"odd", "abcde"}};
+    int64_t begin = 0;
+    const auto head = netcdf_header_bytes(format, nx, ny, nrec, attrs, &begin);
+    std::vector<unsigned char> file(static_cast<size_t>(begin), 0);
+    std::memcpy(file.data(), head.data(), head.size());
+    for (int t = 0; t < nrec; ++t)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const double v = 1e6 * t + 1e3 * y + x + 0.25;
+                uint64_t bits;
+                std::memcpy(&bits, &v, 8);
+                for (int sh = 56; sh >= 0; sh -= 8) file.push_back(static_cast<unsigned char>(bits >> sh));
+            }
+    std::ofstream out(path, std::ios::binary);
+    out.write(reinterpret_cast<const char*>(file.data()), static_cast<std::streamsize>(file.size()));
+    return out.good() ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 7 && std::string(argv[1]) == "--write-file")
+        return write_file(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6]));
     config_tests();
     if (argc > 1 && std::string(argv[1]) == "--gpu") {
         MPI_Init(&argc, &argv);

@@ -107,6 +107,13 @@ int csim_field_download_interior_async(const csim_field* f, double* host_dense_p
  * (the NetCDF wire order) by a kernel, then copied to pinned host memory, asynchronously on the
  * context stream.  The host bytes can be written to a CDF-5 file as they are. */
 int csim_field_download_interior_be_async(const csim_field* f, void* host_dense_pinned);
+/* Snapshot hand-off that does not hold up the time loop (src/main.cpp:96-99 → src/io.cpp:411-418): the
+ * de-haloed tile is packed into one of two dense device staging buffers on the context stream (≈ 1 ms at
+ * 16384^2), optionally byte-swapped to big-endian, and a separate copy stream moves it to pinned host
+ * memory while the time steps queued after this call run.  *event completes when the host buffer is
+ * filled: pass it to csim_event_wait (which also releases it).  A third snapshot waits (on the device)
+ * for the first one's copy. */
+int csim_field_snapshot_async(const csim_field* f, void* host_dense_pinned, int big_endian, void** event);
 /* Record an event after everything queued on the context stream so far; csim_event_wait blocks the
  * calling host thread until that point is reached (and releases the event).  Lets a writer thread
  * wait for one snapshot copy without waiting for the time steps queued behind it. */
@@ -122,6 +129,11 @@ int csim_field_set(csim_field* f, int i, int j, double value);
 int csim_field_swap(csim_field* a, csim_field* b);
 /* std::copy(u.data → tmp.data) — src/main.cpp:104 (whole padded tile, device to device). */
 int csim_field_copy(const csim_field* src, csim_field* dst);
+/* Best effort: restrict the calling thread to the CPUs of the NUMA node the GPU `device` hangs off
+ * (sysfs numa_node of its PCI function), so that pinned buffers it allocates next — first touch — and its
+ * copies stay node-local when all GPUs of a box move tiles at once.  *node receives the node or -1 when
+ * the platform reports none (then nothing is changed).  Never fails on a missing sysfs entry. */
+int csim_bind_thread_to_device_numa(int device, int* node);
 /* pinned host memory for upload/download buffers */
 int csim_host_alloc(size_t bytes, void** out);
 int csim_host_free(void* p);
@@ -285,6 +297,19 @@ int csim_halo_stats_get(csim_ctx* ctx, csim_halo_stats* out);
 int csim_initial_condition_host(double* host_padded, const csim_decomp* dec, int halo,
                                 int nx_global, int ny_global, double dx, double dy, int preset,
                                 double A, double sigma_frac, double xc_frac, double yc_frac);
+
+/* The same initial condition generated ON THE DEVICE, into the interior of `f` (ghost cells untouched),
+ * asynchronously on the context stream — src/init.cpp:12-47 without the host loop and the upload.
+ * Bit-identical to csim_initial_condition_host: same operation order, and exp() is the host libm's
+ * table-driven algorithm restated for the device (csrc/exp_libm.cuh).  Which rounding sequence the
+ * host's exp() uses depends on its build (FMA-contracted or not); csim_exp_variant() probes it once:
+ * 1 = FMA variant, 0 = plain variant, -1 = neither matches, in which case this call returns
+ * CSIM_ERR_UNSUPPORTED and the caller keeps the host path.  `dec` supplies the offsets, `f` dx and dy. */
+int csim_initial_condition_device(csim_field* f, const csim_decomp* dec, int nx_global, int ny_global,
+                                  int preset, double A, double sigma_frac, double xc_frac, double yc_frac);
+int csim_exp_variant(void);
+/* The restated exp() itself on the host (variant 1 or 0), for tests against the host libm. */
+double csim_exp_restated(double x, int variant);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,63 @@
+"""The restated exp() behind the device-side initial condition (csrc/exp_libm.cuh) against the host libm,
+bit for bit, on the CPU.  math.exp IS the host libm's exp (CPython calls it directly); numpy's exp is not
+(it has its own SIMD loops), so it is not used here.
+
+What is pinned: whichever variant csim_exp_variant() reports (1: FMA-contracted build of glibc's exp,
+0: plain build) reproduces math.exp on every input tried — random arguments over the whole range where
+exp is finite or underflows, the special-case boundaries (|x| < 2^-54, 512, 1024, the subnormal results
+below -708.39, -inf, NaN), and the arguments the Gaussian initial condition really produces."""
+import math
+import random
+import struct
+
+import pytest
+
+
+def _bits(x):
+    return struct.unpack("<Q", struct.pack("<d", x))[0]
+
+
+def _same(a, b):
+    return _bits(a) == _bits(b) or (a != a and b != b)
+
+
+def test_exp_table_is_the_generated_one(csim):
+    """exp_table.inc is what tools/gen_exp_table.py derives from 2^(k/128) with 80-digit arithmetic."""
+    import os
+    import re
+    import subprocess
+    import sys
+    from conftest import ROOT
+    inc = os.path.join(ROOT, "climate-sim-mpi-cpp_b200", "csrc", "exp_table.inc")
+    before = open(inc).read()
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_exp_table.py")], check=True, capture_output=True)
+    assert open(inc).read() == before
+    words = re.findall(r"0x([0-9a-f]{16})ull", before)
+    assert len(words) == 256 and words[0] == "0" * 16 and words[1] == "3ff0000000000000"
+
+
+def test_restated_exp_matches_host_libm(csim):
+    v = csim.exp_variant()
+    if v < 0:
+        pytest.skip("host libm exp() is neither restated variant: the device initial condition is disabled here")
+    rng = random.Random(42)
+    xs = [0.0, -0.0, -1e-300, -5e-324, -1e-17, -2.0 ** -54, -2.0 ** -53, -1.0, -100.0, -511.9999, -512.0, -512.0001,
+          -700.0, -708.3964185322641, -708.4, -709.0, -720.0, -744.0, -745.0, -745.13, -745.14, -746.0, -1023.9,
+          -1024.0, -1e5, -math.inf, 1e-9, 0.5, 1.0, 88.0, 511.0, 512.0, 600.0, 709.7, math.nan]
+    xs += [rng.uniform(-760.0, 5.0) for _ in range(400_000)]
+    xs += [rng.uniform(-2.0, 0.0) for _ in range(200_000)]
+    xs += [-(10.0 ** rng.uniform(-20, 3)) for _ in range(100_000)]
+    for n, frac in ((64, 0.05), (512, 0.05), (16384, 0.05), (512, 0.004)):  # -r2 / (2 sig^2) on a cell-centre grid
+        sig, c = frac * n, 0.5 * n
+        for i in range(0, n, max(1, n // 4096)):
+            x = (i + 0.5) - c
+            xs.append(-(x * x + (17.5 - c) ** 2) / (2.0 * sig * sig))
+    bad = [x for x in xs if not _same(csim.exp_restated(x, v), math.exp(x) if x < 709.78 or x != x else math.inf)]
+    assert not bad, (v, len(bad), bad[:5])
+
+
+def test_the_other_variant_differs(csim):
+    """The two rounding sequences are really different functions (so the probe decides something)."""
+    rng = random.Random(7)
+    xs = [rng.uniform(-700.0, 0.0) for _ in range(100_000)]
+    assert any(not _same(csim.exp_restated(x, 0), csim.exp_restated(x, 1)) for x in xs)

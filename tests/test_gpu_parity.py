@@ -387,6 +387,53 @@ def test_minmax_and_health(csim, ctx):
     assert f.health()[1] == 2
 
 
+# ---- initial condition generated on the device (N4): src/init.cpp:12-47 ---------------------------
+
+def _ic_pair(csim, ctx, size, rank, nxg, nyg, dx, dy, A, sf, xc, yc):
+    dec = csim.Decomp2D.init(size, rank, nxg, nyg)
+    want = csim.initial_condition_host(dec, 1, dx, dy, "gaussian_hotspot", A, sf, xc, yc)
+    f = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, dx, dy)
+    csim.initial_condition_device(f, dec, "gaussian_hotspot", A, sf, xc, yc)
+    got = f.download()
+    f.close()
+    return got, want
+
+
+def test_initial_condition_device_matches_host(csim, ctx):
+    """Tiles of 1-, 4- and 8-rank decompositions (offsets, remainders), non-unit spacing, narrow hotspots
+    whose tails underflow through the subnormal range to zero, an off-centre hotspot: the device tile equals
+    the host tile bit for bit, ghost ring (untouched zeros) included."""
+    if csim.exp_variant() < 0:
+        pytest.skip("host libm exp() is not one of the restated variants: device path disabled")
+    cases = [(1, 64, 64, 1.0, 1.0, 1.0, 0.05, 0.5, 0.5), (4, 513, 300, 1.0, 1.0, 2.5, 0.05, 0.5, 0.5),
+             (8, 1000, 777, 0.3, 0.7, 1.0, 0.05, 0.3, 0.8), (4, 2048, 2048, 1.0, 1.0, 1.0, 0.004, 0.5, 0.5),
+             (2, 4096, 512, 0.5, 2.0, -3.0, 0.0125, 0.1, 0.9), (1, 7, 5, 1.0, 1.0, 1.0, 0.5, 0.5, 0.5)]
+    for (size, nxg, nyg, dx, dy, A, sf, xc, yc) in cases:
+        for rank in range(size):
+            got, want = _ic_pair(csim, ctx, size, rank, nxg, nyg, dx, dy, A, sf, xc, yc)
+            assert bits_equal(got, want), (size, rank, nxg, nyg, sf)
+    f = csim.Field(ctx, 8, 8, 1, 1.0, 1.0)
+    csim.initial_condition_device(f, csim.Decomp2D.single(8, 8), "constant_zero")  # no-op, init.cpp:39-40
+    assert not f.download().any()
+    with pytest.raises(RuntimeError, match="Unknown IC preset"):
+        csim.initial_condition_device(f, csim.Decomp2D.single(8, 8), "checkerboard")
+
+
+def test_initial_condition_device_full_size(csim, ctx):
+    """configs[2]'s 16384^2 tile: all 2.7e8 cells, device against host."""
+    if csim.exp_variant() < 0:
+        pytest.skip("host libm exp() is not one of the restated variants: device path disabled")
+    n = 16384
+    dec = csim.Decomp2D.single(n, n)
+    want = csim.initial_condition_host(dec, 1, 1.0, 1.0)
+    f = csim.Field(ctx, n, n, 1, 1.0, 1.0)
+    csim.initial_condition_device(f, dec)
+    got = f.download()
+    f.close()
+    mismatches = int(np.count_nonzero(got.view(np.uint64) != want.view(np.uint64)))
+    assert mismatches == 0, f"{mismatches} of {n * n} cells differ"
+
+
 # ---- multi-GPU halo exchange (needs >= 2 devices; the 1-GPU box skips) ---------------------------
 
 def _rank_worker(csim, size, rank, uid, nxg, nyg, steps, phys, bc, flags, results, errors):
@@ -483,10 +530,16 @@ def test_multi_process_parity_under_torchrun():
 @pytest.mark.parametrize("env", [{"CSIM_TB_MAXT": "4"}, {"CSIM_TB_MAXT": "2"}, {"CSIM_TB_MAXT": "1"},
                                  {"CSIM_TB_MAXT": "3", "CSIM_TB_CHUNK": "7", "CSIM_TB_EDGE_SPLIT": "3"},
                                  {"CSIM_TB_MAXT": "4", "CSIM_TB_CHUNK": "500", "CSIM_TB_EDGE_SPLIT": "1",
-                                  "CSIM_TB_PF": "0"}])
+                                  "CSIM_TB_PF": "0"},
+                                 {"CSIM_TB_MAXT": "3", "CSIM_TB_KERNEL": "reg"},
+                                 {"CSIM_TB_MAXT": "4", "CSIM_TB_KERNEL": "reg", "CSIM_TB_CHUNK": "33"},
+                                 {"CSIM_TB_MAXT": "3", "CSIM_TB_DIV_MAXT": "3"},
+                                 {"CSIM_TB_MAXT": "4", "CSIM_TB_DIV_MAXT": "2", "CSIM_TB_CHUNK": "21"}])
 def test_every_blocking_depth_and_chunking_matches_golden(env):
-    """The sweep is instantiated for T = 1..4; the default run uses T <= 3.  Each depth, odd chunk
-    heights and edge splits must give the same bits (the knobs are read once per process → subprocess)."""
+    """The sweep is instantiated for T = 1..4 in two builds — level-0 rows staged through shared memory by
+    TMA (the default for T >= 3) and register-only (CSIM_TB_KERNEL=reg; always for T <= 2) — and with
+    IEEE division up to T = 3 (CSIM_TB_DIV_MAXT).  Each depth and build, odd chunk heights and edge splits
+    must give the same bits (the knobs are read once per process → subprocess)."""
     import os
     import subprocess
     import sys

@@ -18,5 +18,4 @@ P="python bench.py --tile 16384 --steps 2 --warmup 1 --inner 12 --no-cpu-baselin
 ncu --set full --clock-control none --import-source on -k regex:k_step_tb -s 4 -c 2 -o $O/tb3_16384 -f $P > $O/ncu_full.log 2>&1
 ncu -i $O/tb3_16384.ncu-rep --page raw --csv > $O/tb3_16384_raw.csv 2>/dev/null
 ncu -i $O/tb3_16384.ncu-rep --page source --csv --print-source sass > $O/tb3_16384_source.csv 2>/dev/null
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -q -x -k "golden_case or ragged or boundary_matches or chunking_is_invisible" > $O/memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/memcheck.log
 ls -la $O
