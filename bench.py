@@ -213,7 +213,7 @@ def parity_windows(dec, w):
     return sorted(set(pts)), w
 
 
-def check_parity(csim, co, port, got, dec, nxg, nyg, phys, bc_codes, steps, w=64):
+def check_parity(csim, co, port, got, dec, nxg, nyg, phys, bc_codes, steps, w=64, dx=1.0, dy=1.0):
     """Bit-compare windows of `got` (this rank's interior after `steps` time steps from the initial condition)
     with the CPU oracle advanced on the sub-domain around each window.  The sub-domain reaches `steps` cells
     beyond the window (the dependency cone of `steps` 5-point updates) or to the physical boundary; its cut
@@ -227,17 +227,62 @@ def check_parity(csim, co, port, got, dec, nxg, nyg, phys, bc_codes, steps, w=64
         x0, x1 = max(gx - steps, 0), min(gx + w + steps, nxg)
         sub = np.zeros((y1 - y0 + 2, x1 - x0 + 2))  # padded; ghosts outside the physical domain stay 0
         iy0, iy1, ix0, ix1 = max(y0 - 1, 0), min(y1 + 1, nyg), max(x0 - 1, 0), min(x1 + 1, nxg)
-        ic = csim.initial_condition_host(csim.Decomp2D.window(nxg, nyg, ix0, iy0, ix1 - ix0, iy1 - iy0), 0, 1.0, 1.0)
+        ic = csim.initial_condition_host(csim.Decomp2D.window(nxg, nyg, ix0, iy0, ix1 - ix0, iy1 - iy0), 0, dx, dy)
         sub[iy0 - (y0 - 1):iy1 - (y0 - 1), ix0 - (x0 - 1):ix1 - (x0 - 1)] = ic
         bc = (bc_codes[0] if x0 == 0 else 2, bc_codes[1] if x1 == nxg else 2,
               bc_codes[2] if y0 == 0 else 2, bc_codes[3] if y1 == nyg else 2)
-        sp = co.SimParams(nx=x1 - x0, ny=y1 - y0, steps=steps, out_every=steps, bc=bc, **phys)
+        sp = co.SimParams(nx=x1 - x0, ny=y1 - y0, dx=dx, dy=dy, steps=steps, out_every=steps, bc=bc, **phys)
         want = port.run(sp, u0_padded=sub)["final"]
         a = np.ascontiguousarray(got[y:y + w, x:x + w])
         b = np.ascontiguousarray(want[gy - y0:gy - y0 + w, gx - x0:gx - x0 + w])
         if not np.array_equal(a.view(np.uint64), b.view(np.uint64)):
             bad += 1
     return len(pts), bad
+
+
+def shared_file_check(rank, world, local_rank, dist):
+    """N > 1 only: the C++ driver (host/build/climate_sim_b200) run as one process per GPU of this box —
+    RANK/WORLD_SIZE + rendezvous file, no MPI launcher — on a small grid with mixed boundaries; every rank
+    writes its window of the SAME CDF-5 file (src/io.cpp:402-424).  Rank 0 reads the file back and compares
+    every frame with the single-rank CPU oracle, bit for bit."""
+    import shutil
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "climate-sim-mpi-cpp_b200", "host", "build", "climate_sim_b200")
+    if not os.path.exists(exe):
+        return None
+    box = [tempfile.mkdtemp(prefix="csim_shared_file_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    work = box[0]
+    nx, ny, steps, every = 301 + 64 * world, 260 + 32 * world, 50, 10
+    cli = [f"--nx={nx}", f"--ny={ny}", "--D=0.05", "--vx=-0.5", "--vy=0.25", f"--steps={steps}", f"--out_every={every}",
+           "--bc.right=neumann", "--bc.bottom=periodic"]
+    env = dict(os.environ)
+    env.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local_rank), CSIM_JOB_ID=os.path.basename(work),
+               CSIM_RENDEZVOUS=os.path.join(work, "rendezvous"))
+    r = subprocess.run([exe] + cli, cwd=work, env=env, capture_output=True, text=True, timeout=600)
+    rcs = [None] * world
+    dist.all_gather_object(rcs, (r.returncode, (r.stdout + r.stderr)[-400:] if r.returncode else ""))
+    out = None
+    if rank == 0:
+        out = {"ranks": world, "grid": f"{nx}x{ny}", "frames": steps // every, "bit_identical": False,
+               "what": "climate_sim_b200 as one process per GPU, all ranks writing disjoint windows of one CDF-5 "
+                       "file; frames compared with the single-rank CPU oracle"}
+        if any(rc for rc, _ in rcs):
+            out["error"] = "; ".join(f"rank {i}: rc {rc} {msg}" for i, (rc, msg) in enumerate(rcs) if rc)
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from cdf5_reader import read_cdf5
+            from oracle import cpu_oracle as co
+            if not co.available("port"):
+                co.build()
+            f = read_cdf5(os.path.join(work, "outputs", "snapshots.nc"))
+            p = co.SimParams(nx=nx, ny=ny, D=0.05, vx=-0.5, vy=0.25, steps=steps, out_every=every, bc=(0, 1, 2, 0))
+            want = co.Oracle("port").run(p)["frames"]
+            out["bit_identical"] = bool(f["numrecs"] == steps // every and f["data"].shape == want.shape and
+                                        np.array_equal(f["data"].view(np.uint64), want.view(np.uint64)))
+        shutil.rmtree(work, ignore_errors=True)
+    return out
 
 
 def run_ours(args):
@@ -278,15 +323,14 @@ def run_ours(args):
     params = csim.make_step_params(PHYS["D"], PHYS["vx"], PHYS["vy"], PHYS["dt"], bcs, dec)
     host_in = ctx.pinned_empty((dec.ny_local + 2, dec.nx_local + 2))
     host_in[:] = 0.0
-    csim.initial_condition_host(dec, 1, 1.0, 1.0, out=host_in)
+    csim.initial_condition_host(dec, 1, args.dx, args.dy, out=host_in)
     host_out = [ctx.pinned_empty((dec.ny_local, dec.nx_local)) for _ in range(2)]
-    u = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
-    tmp = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, 1.0, 1.0)
+    u = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, args.dx, args.dy)
+    tmp = csim.Field(ctx, dec.nx_local, dec.ny_local, 1, args.dx, args.dy)
     u.upload(host_in)
     halo_path = "none"
     if world > 1:
-        halo_path = ("T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block over NVLink, unpack "
-                     "kernel; hidden behind the interior sweep; the block loop replayed as a CUDA graph")
+        halo_path = "decided on the first window (csim_halo_path)"
 
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
@@ -357,6 +401,13 @@ def run_ours(args):
     # ---- halo timeline (N > 1): one window run eagerly with timestamps around every exchange -------------
     halo = None
     if world > 1:
+        halo_path = {"peer": "T-line bands stored straight into the neighbours' ghost lines over NVLink (tiles mapped "
+                             "with CUDA IPC) by single-warp CTAs that co-reside with the interior sweep, one flag per "
+                             "neighbour; hidden behind the interior sweep; NCCL only for bootstrap",
+                     "nccl": "T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block over NVLink, unpack "
+                             "kernel; hidden behind the interior sweep"}.get(csim.halo_path(ctx), csim.halo_path(ctx))
+        if os.environ.get("CSIM_GRAPH") == "1":
+            halo_path += "; block loop replayed as a CUDA graph"
         barrier()
         csim.halo_profile(ctx, True)
         csim.run_steps(u, tmp, params, dec, inner)
@@ -376,8 +427,11 @@ def run_ours(args):
             "frac_of_nvlink": (wire / (us_max * 1e-6) / 1e9 / NVLINK_GBS_PER_DIRECTION) if us_max > 0 else None,
             "overlap_fraction": -reduce_max(-st["overlap_fraction"]),  # the worst rank
             "us_frame_sweep": reduce_max(st["frame_us"]), "us_interior_sweep": reduce_max(st["interior_us"]),
-            "note": "pack kernel + grouped NCCL send/recv + unpack kernel, CUDA events on the exchange stream, one "
-                    "eager (un-graphed) window; max over ranks; overlap_fraction = share of the exchange time that "
+            "us_exchange_done_to_frame_start": reduce_max(st["wait_for_interior_us"]),
+            "path": csim.halo_path(ctx),
+            "note": "one exchange = everything between the end of the frame sweep and the start of the next one on the "
+                    "exchange stream (peer: store kernel + flag wait; nccl: pack + grouped send/recv + unpack), CUDA "
+                    "events, one eager window; max over ranks; overlap_fraction = share of the exchange time that "
                     "lies inside the concurrently running interior sweep (latency-bound: a 393 KB band is 0.4 us of "
                     "wire time at 900 GB/s)",
         }
@@ -454,7 +508,8 @@ def run_ours(args):
             csim.run_steps(u, tmp, pp, dec, K)
             u.download_interior_async(host_out[0])
             ctx.sync()
-            w, b = check_parity(csim, co, port, host_out[0], dec, nxg, nyg, phys, bcs.as_tuple(), K)
+            w, b = check_parity(csim, co, port, host_out[0], dec, nxg, nyg, phys, bcs.as_tuple(), K, dx=args.dx,
+                                dy=args.dy)
             n_win += w
             n_bad += b
             sets.append(name)
@@ -470,6 +525,18 @@ def run_ours(args):
                       flush=True)
             raise SystemExit(3)
 
+    shared_file = None
+    if world > 1 and not args.no_parity:
+        barrier()
+        shared_file = shared_file_check(rank, world, local_rank, dist)
+        if rank == 0 and shared_file is not None and not shared_file["bit_identical"]:
+            print(json.dumps({"metric": METRIC, "shared_file": shared_file,
+                              "error": "the ranks' shared snapshot file differs from the oracle"}), flush=True)
+        bad_file = [shared_file is not None and not shared_file["bit_identical"]] if rank == 0 else [None]
+        dist.broadcast_object_list(bad_file, src=0)
+        if bad_file[0]:
+            raise SystemExit(4)
+
     # ---- roofline of the dominant kernel: the fused sweep k_step_tb, which advances T steps per launch ----
     # With all-periodic boundaries no boundary kernels run, so on one GPU the timed region is exactly
     # the sweeps; with N>1 the pack/NCCL/unpack and frame launches share the region (sweep count is
@@ -477,6 +544,9 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     T = csim.steps_per_sweep()
     sweeps_per_window = inner // T + (1 if inner % T else 0)
+    if world == 1 and launches % args.steps == 0 and launches > 0:
+        sweeps_per_window = launches // args.steps  # one GPU, frozen ghosts: every launch of the window is a sweep
+        T = max(1, round(inner / sweeps_per_window))  # (the IEEE-division mode sweeps one step at a time)
     sweeps = args.steps * sweeps_per_window
     launch_ms = ms / sweeps
     steps_per_launch = inner / sweeps_per_window
@@ -493,7 +563,8 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": f"csim::k_step_tb<T={T}> (fused diffusion+advection sweep, {T} steps per launch"
+                "kernel": f"csim::{csim.sweep_kernel()}<T={T}> (fused diffusion+advection sweep, {T} steps per launch"
+                          + (", level-0 rows staged through shared memory by TMA bulk copies" if csim.sweep_kernel() == "k_step_tbs" else "")
                           + (", y-advection term dropped: vy == +0.0)" if dropped else ")"),
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": launch_ms,
                 "steps_per_launch": steps_per_launch, "frac_of_nominal_8TBs": achieved / 8000.0,
@@ -519,6 +590,11 @@ def run_ours(args):
                                f"Dirichlet, right/top Neumann, decomp {{{dims[0]},{dims[1]}}}, tile {dec.nx_local}x{dec.ny_local}"
                                if args.bc == "dn" else
                                f"{nxg}x{nyg} global (strong scaling), periodic BCs, decomp {{{dims[0]},{dims[1]}}}")
+        if args.dx != 1.0 or args.dy != 1.0:
+            cfg["workload"] += f"; dx={args.dx}, dy={args.dy}"
+            cfg["spacing"] = {"dx": args.dx, "dy": args.dy,
+                              "mode": "IEEE division (the spacing is not a power of two)" if not dropped and
+                              csim.steps_per_sweep() and (args.dx, args.dy) != (1.0, 1.0) else "reciprocal"}
         cfg.update({
             "halo_exchange": halo_path,
             "arithmetic": ("vy == +0.0 on a scanned-clean field: y-advection term dropped, 11 FP64 ops per "
@@ -532,7 +608,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.global_size else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "halo": halo,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "halo": halo, "shared_file": shared_file,
             "all_terms": {"value": gen_value, "unit": "cell-updates/s", "vx": PHYS_ALL_TERMS["vx"],
                           "vy": PHYS_ALL_TERMS["vy"], "steps": gen_steps, "ms_per_step": ms_gen / gen_steps,
                           "clocks": clocks_gen,
@@ -565,6 +641,9 @@ def main():
     ap.add_argument("--parity-steps", type=int, default=10, help="time steps of the parity run (>= 2T+1)")
     ap.add_argument("--global-size", type=int, default=0,
                     help="strong scaling: fixed NxN global grid split over the ranks (32768 = configs[3])")
+    ap.add_argument("--dx", type=float, default=1.0, help="grid spacing in x (a spacing that is not a power of two "
+                    "makes the kernels divide: IEEE-division mode, src/diffusion.cpp:12-13)")
+    ap.add_argument("--dy", type=float, default=1.0)
     ap.add_argument("--bc", choices=["periodic", "dn"], default="periodic",
                     help="dn: left/bottom Dirichlet, right/top Neumann (configs[3])")
     args = ap.parse_args()

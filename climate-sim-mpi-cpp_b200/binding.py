@@ -75,7 +75,7 @@ class HaloStats(C.Structure):
     """csim_halo_stats"""
     _fields_ = [("blocks", C.c_int), ("bytes_per_exchange", C.c_size_t), ("first_exchange_us", C.c_double),
                 ("exchange_us", C.c_double), ("overlap_fraction", C.c_double), ("frame_us", C.c_double),
-                ("interior_us", C.c_double), ("total_ms", C.c_double)]
+                ("interior_us", C.c_double), ("total_ms", C.c_double), ("wait_for_interior_us", C.c_double)]
 
 
 class StepParams(C.Structure):
@@ -159,6 +159,8 @@ def lib():
                                             C.c_double, C.c_double],
             "csim_initial_condition_device": [vp, C.POINTER(_Decomp), C.c_int, C.c_int, C.c_int, C.c_double,
                                               C.c_double, C.c_double, C.c_double],
+            "csim_device_count": [ip],
+            "csim_field_download_window": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
             "csim_halo_profile": [vp, C.c_int],
             "csim_field_snapshot_async": [vp, vp, C.c_int, C.POINTER(C.c_void_p)],
             "csim_bind_thread_to_device_numa": [C.c_int, ip],
@@ -182,6 +184,11 @@ def lib():
         L.csim_safe_dt.restype = C.c_double
         L.csim_abi_version.restype = C.c_int
         L.csim_steps_per_sweep.restype = C.c_int
+        if hasattr(L, "csim_sweep_kernel"):
+            L.csim_sweep_kernel.restype = C.c_char_p
+        if hasattr(L, "csim_halo_path"):
+            L.csim_halo_path.argtypes = [vp]
+            L.csim_halo_path.restype = C.c_char_p
         if hasattr(L, "csim_exp_variant"):
             L.csim_exp_variant.restype = C.c_int
             L.csim_exp_restated.argtypes = [C.c_double, C.c_int]
@@ -334,6 +341,12 @@ class Field:
         """De-haloed tile as big-endian doubles (NetCDF wire order) into a pinned buffer, asynchronously."""
         assert out.size == self.nx_local * self.ny_local and out.flags["C_CONTIGUOUS"]
         _check(lib().csim_field_download_interior_be_async(self._h, out.ctypes.data_as(C.c_void_p)))
+
+    def download_window(self, x0: int, y0: int, w: int, h: int) -> np.ndarray:
+        """A w x h window, first cell (x0, y0) in interior coordinates (csim_field_download_window)."""
+        out = np.empty((h, w))
+        _check(lib().csim_field_download_window(self._h, x0, y0, w, h, _ptr(out)))
+        return out
 
     def download_interior_async(self, out: np.ndarray):
         _check(lib().csim_field_download_interior_async(self._h, _ptr(out)))
@@ -523,6 +536,10 @@ def initial_condition_device(f: "Field", dec: Decomp2D, preset="gaussian_hotspot
                                                presets[preset], A, sigma_frac, xc_frac, yc_frac))
 
 
+def sweep_kernel() -> str:
+    return lib().csim_sweep_kernel().decode() if hasattr(lib(), "csim_sweep_kernel") else "k_step_tb"
+
+
 def exp_variant() -> int:
     """Which restated variant of exp() matches the host libm: 1 FMA, 0 plain, -1 neither."""
     return int(lib().csim_exp_variant())
@@ -535,6 +552,11 @@ def exp_restated(x: float, variant: int) -> float:
 def halo_profile(ctx: "Context", enable=True):
     """The next run_steps on a tile with neighbours runs eagerly with timestamps (csim_halo_profile)."""
     _check(lib().csim_halo_profile(ctx._h, 1 if enable else 0))
+
+
+def halo_path(ctx: "Context") -> str:
+    """"peer", "nccl" or "none": the halo path the last run_steps on this context used."""
+    return lib().csim_halo_path(ctx._h).decode() if hasattr(lib(), "csim_halo_path") else "nccl"
 
 
 def halo_stats(ctx: "Context") -> dict:

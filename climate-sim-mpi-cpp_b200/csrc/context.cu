@@ -113,10 +113,22 @@ int csim_ctx_create(int device, csim_ctx** out) {
     return CSIM_OK;
 }
 
+int csim_device_count(int* count) {
+    CSIM_REQUIRE(count != nullptr, CSIM_ERR_INVALID, "csim_device_count: null argument");
+    *count = 0;
+    const cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(CSIM_ERR_CUDA, std::string("csim_device_count: ") + cudaGetErrorString(e));
+    }
+    return CSIM_OK;
+}
+
 int csim_ctx_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    peer_teardown(c);
     run_state_destroy(c);  // graphs hold NCCL kernels: they go before the communicator
     if (c->comm) csim_comm_destroy(c);
     // tiles that outlive their context (garbage-collection order in a host language) are orphaned:
@@ -164,6 +176,8 @@ int csim_sync(csim_ctx* c) {
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_copy));
+    if (c->h_err && *c->h_err)
+        return fail(CSIM_ERR_TIMEOUT, "csim_sync: a neighbour's halo did not arrive within the bounded wait");
     return CSIM_OK;
 }
 
@@ -218,6 +232,10 @@ int csim_field_destroy(csim_field* f) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->stream_x);
+    // a tile the neighbours have mapped takes the peer links down with it: a later tile may get the same
+    // address, and storing through stale mappings would corrupt the neighbours
+    if (f->ctx->peer_ready && (f->base == f->ctx->peer_tile[0] || f->base == f->ctx->peer_tile[1]))
+        peer_teardown(f->ctx);
     if (f->base) cudaFree(f->base);
     delete f;
     return CSIM_OK;
@@ -314,6 +332,16 @@ int csim_field_download_interior(const csim_field* f, double* host) {
                  "csim_field_download_interior: null argument");
     return copy2d(f, host, f->nx * sizeof(double), f->interior(), f->pitch * sizeof(double), f->nx, f->ny,
                   cudaMemcpyDeviceToHost, true);
+}
+int csim_field_download_window(const csim_field* f, int x0, int y0, int w, int h, double* host) {
+    CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID, "csim_field_download_window: null argument");
+    CSIM_REQUIRE(w >= 0 && h >= 0, CSIM_ERR_INVALID, "csim_field_download_window: negative extent");
+    CSIM_REQUIRE(x0 >= -f->h && y0 >= -f->h && static_cast<int64_t>(x0) + w <= static_cast<int64_t>(f->nx) + f->h &&
+                     static_cast<int64_t>(y0) + h <= static_cast<int64_t>(f->ny) + f->h,
+                 CSIM_ERR_RANGE, "Field index out of range");
+    return copy2d(f, host, static_cast<size_t>(w) * sizeof(double),
+                  f->interior() + static_cast<int64_t>(y0) * f->pitch + x0, f->pitch * sizeof(double),
+                  static_cast<size_t>(w), static_cast<size_t>(h), cudaMemcpyDeviceToHost, true);
 }
 int csim_field_download_interior_async(const csim_field* f, double* host) {
     CSIM_REQUIRE(f != nullptr && host != nullptr, CSIM_ERR_INVALID,

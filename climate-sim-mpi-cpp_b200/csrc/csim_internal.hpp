@@ -41,6 +41,22 @@ struct csim_ctx {
     size_t stage_doubles = 0;
     double* d_wide = nullptr;  // wide-halo exchange staging: 8 send + 8 recv regions
     size_t wide_doubles = 0;
+    // peer-memory halo (halo.cu): the up to eight neighbours' tiles and flag words mapped into this process
+    struct PeerLink {
+        int rank = -1;
+        double* tile[2] = {nullptr, nullptr};  // the neighbour's two tile allocations (its u, tmp at setup)
+        long long pitch = 0;
+        int nx = 0, ny = 0;
+        unsigned* flags = nullptr;             // the neighbour's flag words
+        bool ipc = false;                      // mapped with cudaIpcOpenMemHandle (else same-process pointers)
+    };
+    PeerLink peer[8];
+    bool peer_ready = false;
+    bool peer_failed = false;                   // mapping was refused once: stay on the NCCL path
+    double* peer_tile[2] = {nullptr, nullptr};  // this rank's two allocations, in the order given at setup
+    unsigned* d_flags = nullptr;                // [0..7] written by the neighbours, [8] ticket, [9] pushes, [10] waits
+    unsigned* h_err = nullptr;                  // pinned, mapped: set by the wait kernel before it traps
+    unsigned* d_err = nullptr;
     // snapshot hand-off (context.cu, csim_field_snapshot_async): two dense staging buffers, a copy stream
     cudaStream_t stream_copy = nullptr;
     double* d_snapbuf[2] = {nullptr, nullptr};
@@ -83,6 +99,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 bool is_pow2(double x);
 
 void run_state_destroy(csim_ctx* c);  // halo.cu
+int peer_teardown(csim_ctx* c);        // halo.cu
 struct StepK;
 enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2 };
 int tb_max_T();

@@ -14,6 +14,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -197,6 +199,362 @@ static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     return CSIM_OK;
 }
 
+// ---- peer-memory exchange: the bands go straight into the neighbours' ghost lines -------------------
+// Why these kernels are "light".  The interior sweep holds 3 CTAs x 128 threads x 168 registers = 64 512 of
+// an SM's 65 536 registers for its whole duration, and with 320-row chunks a CTA lives ~250 us.  Any
+// helper kernel that needs more than the 1 024 registers left over has to wait for interior CTAs to exit
+// — NCCL's send/recv kernel (one fat CTA) in practice until the TAIL of the interior sweep: measured 770 us
+// per exchange at 16384^2 per GPU, on the frame → exchange → frame chain that bounds the block time
+// (profiles/r02_multigpu.md).  A CTA of ONE warp with at most 32 registers per thread is exactly 1 024
+// registers, so these kernels start at once beside a full interior sweep.
+struct PushRegion {
+    int x0, y0, w, h;     // source region in this rank's tile (interior coordinates)
+    double* dst;          // neighbour's cell that receives the region's first cell (mapped pointer)
+    long long dst_pitch;  // neighbour's row pitch
+    unsigned* flag;       // neighbour's flag word for this direction, nullptr: no neighbour
+};
+struct PushTable {
+    PushRegion r[8];
+};
+// words of csim_ctx::d_flags: [0..7] "halo arrived" flags written by the neighbours, then this rank's own
+// counters, then [16..23] "ready to receive" flags written by the neighbours
+enum { kCtlTicket = 8, kCtlPushSeq = 9, kCtlWaitSeq = 10, kCtlReadySeq = 11, kCtlReadyFlags = 16, kCtlWords = 32 };
+
+// Store all regions into the neighbours' tiles; the last CTA to finish (ticket) publishes the sequence
+// number of this push in every neighbour's flag word.  The sequence number lives in device memory so
+// that a CUDA-graph replay pushes the right one.
+__global__ void __maxnreg__(32) k_push_light(const double* __restrict__ u, long long pitch,
+                                                                   PushTable t, unsigned* __restrict__ ctl) {
+    const int lane = threadIdx.x;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        const PushRegion g = t.r[q];
+        if (!g.flag) continue;
+        const int n = g.w * g.h;
+        for (int e = blockIdx.x * 32 + lane; e < n; e += gridDim.x * 32) {
+            const int yy = e / g.w, xx = e - yy * g.w;
+            g.dst[static_cast<long long>(yy) * g.dst_pitch + xx] = u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx];
+        }
+    }
+    __threadfence_system();  // this thread's peer stores are visible system-wide before the ticket
+    __syncwarp();
+    unsigned last = 0, seq = 0;
+    if (lane == 0) {
+        last = atomicAdd(&ctl[kCtlTicket], 1u) == gridDim.x - 1 ? 1u : 0u;
+        if (last) {
+            ctl[kCtlTicket] = 0;  // re-arm for the next push (stream order protects it)
+            seq = ctl[kCtlPushSeq] + 1u;
+            ctl[kCtlPushSeq] = seq;
+            __threadfence_system();
+        }
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    if (last && lane < 8 && t.r[lane].flag) *reinterpret_cast<volatile unsigned*>(t.r[lane].flag) = seq;
+}
+
+// Gate of the frame sweep: wait until every neighbour in `mask` has published this exchange's sequence
+// number.  Bounded: after `timeout_ns` the kernel records which neighbour is missing and traps, which
+// fails every later call on the context instead of sweeping over stale ghost lines.
+__global__ void __maxnreg__(32) k_wait_light(const unsigned* flags, unsigned mask,
+                                                                   unsigned* __restrict__ ctl,
+                                                                   unsigned long long timeout_ns, unsigned* err) {
+    const int k = threadIdx.x;
+    unsigned seq = 0;
+    if (k == 0) {
+        seq = ctl[kCtlWaitSeq] + 1u;
+        ctl[kCtlWaitSeq] = seq;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    if (k < 8 && ((mask >> k) & 1)) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const volatile unsigned* f = flags + k;
+        // seq wraps after 2^32 exchanges; compare as a signed distance
+        while (static_cast<int>(*f - seq) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                *reinterpret_cast<volatile unsigned*>(err) = 1u + static_cast<unsigned>(k);
+                __threadfence_system();
+                __trap();
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
+static void drop_graphs(csim_ctx* c);  // below, with the graph cache
+
+// Handshake at the start of every csim_run_steps call.  Inside a call the double buffering orders the remote
+// stores (see peer_exchange), but the FIRST push of a call may reach a neighbour that has not entered the
+// call yet and is still writing the same tile from its side — an upload, a fill, a stand-alone kernel — which
+// would overwrite the ghost lines just stored (bench.py's parity windows caught exactly that at 16384^2).
+// So every rank first tells its neighbours "everything I queued on this tile before the call is done"
+// (stream order) and waits for the same from them: a barrier among neighbours, one light kernel per call.
+struct ReadyTable {
+    unsigned* flag[8];  // neighbour's ready word for my direction, nullptr: no neighbour
+};
+__global__ void __maxnreg__(32) k_ready_light(ReadyTable t, unsigned* __restrict__ ctl, unsigned long long timeout_ns,
+                                              unsigned* err) {
+    const int k = threadIdx.x;
+    unsigned seq = 0;
+    if (k == 0) {
+        seq = ctl[kCtlReadySeq] + 1u;
+        ctl[kCtlReadySeq] = seq;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    __threadfence_system();
+    if (k < 8 && t.flag[k]) {
+        *reinterpret_cast<volatile unsigned*>(t.flag[k]) = seq;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const volatile unsigned* f = ctl + kCtlReadyFlags + k;
+        while (static_cast<int>(*f - seq) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                *reinterpret_cast<volatile unsigned*>(err) = 101u + static_cast<unsigned>(k);
+                __threadfence_system();
+                __trap();
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
+static unsigned long long peer_timeout_ns() {
+    static const unsigned long long v = [] {
+        const char* e = std::getenv("CSIM_HALO_TIMEOUT_S");
+        const double s = e ? std::atof(e) : 60.0;
+        return static_cast<unsigned long long>((s > 0.0 ? s : 60.0) * 1e9);
+    }();
+    return v;
+}
+
+// Queue the neighbour barrier on `stream` (peer path only).
+static int peer_ready_barrier(csim_ctx* c, cudaStream_t stream) {
+    ReadyTable t;
+    for (int q = 0; q < 8; ++q) {
+        const csim_ctx::PeerLink& L = c->peer[q];
+        t.flag[q] = (L.rank >= 0 && L.flags) ? L.flags + kCtlReadyFlags + (7 - q) : nullptr;
+    }
+    k_ready_light<<<1, 32, 0, stream>>>(t, c->d_flags, peer_timeout_ns(), c->d_err);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    return CSIM_OK;
+}
+
+static bool peer_path_wanted() {
+    static const bool nccl_only = [] {
+        const char* e = std::getenv("CSIM_HALO");
+        return e && std::strcmp(e, "nccl") == 0;
+    }();
+    return !nccl_only;
+}
+static bool peer_tiles_match(const csim_ctx* c, const csim_field* u, const csim_field* tmp) {
+    return c->peer_ready && ((u->base == c->peer_tile[0] && tmp->base == c->peer_tile[1]) ||
+                             (u->base == c->peer_tile[1] && tmp->base == c->peer_tile[0]));
+}
+
+// Peer version of wide_exchange: store this rank's bands of tile `f` into the neighbours' copy of the
+// same tile (their u when f is our u: every rank swaps in step), then gate `stream` on the neighbours'
+// stores into ours.  Double buffering makes the remote stores safe: exchange(n+1) writes the buffer whose
+// ghost lines the neighbour last read in frame(n-1), and we only get here after the neighbour's push(n),
+// which it queued behind its frame(n-1).
+static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream, size_t* bytes_sent) {
+    csim_ctx* c = f->ctx;
+    csim_decomp d = *dec;
+    d.nx_local = f->nx;
+    d.ny_local = f->ny;
+    csim_xregion ps[8], pr8[8];
+    if (int rc = csim_wide_exchange_plan(&d, T, ps, pr8)) return rc;
+    const int slot = f->base == c->peer_tile[0] ? 0 : 1;
+    const bool pl = dec->nbr[CSIM_LEFT] == CSIM_PROC_NULL, pb = dec->nbr[CSIM_BOTTOM] == CSIM_PROC_NULL;
+    PushTable t;
+    unsigned mask = 0;
+    long long wire = 0;
+    int q = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            PushRegion& g = t.r[q];
+            g.x0 = ps[q].x0;
+            g.y0 = ps[q].y0;
+            g.w = ps[q].w;
+            g.h = ps[q].h;
+            g.dst = nullptr;
+            g.dst_pitch = 0;
+            g.flag = nullptr;
+            const csim_ctx::PeerLink& L = c->peer[q];
+            if (ps[q].peer >= 0) {
+                CSIM_REQUIRE(L.rank == ps[q].peer && L.tile[slot] != nullptr, CSIM_ERR_COMM,
+                             "peer_exchange: neighbour not mapped");
+                // my region lands in the neighbour's ghost area on ITS side (-dx,-dy): its own receive rule
+                // with its own tile size (bands keep their along-side origin: the neighbour shares that
+                // physical side with me)
+                const int rx = dx > 0 ? -T : (dx < 0 ? L.nx : (pl ? -1 : 0));
+                const int ry = dy > 0 ? -T : (dy < 0 ? L.ny : (pb ? -1 : 0));
+                double* interior = L.tile[slot] + static_cast<long long>(kLeadY) * L.pitch + kLeadX;
+                g.dst = interior + static_cast<long long>(ry) * L.pitch + rx;
+                g.dst_pitch = L.pitch;
+                g.flag = L.flags + (7 - q);  // the slot of direction (-dx,-dy) in the neighbour's array
+                mask |= 1u << q;
+                wire += static_cast<long long>(g.w) * g.h;
+            }
+            ++q;
+        }
+    if (bytes_sent) *bytes_sent = static_cast<size_t>(wire) * sizeof(double);
+    const unsigned long long timeout_ns = peer_timeout_ns();
+    k_push_light<<<c->sm_count, 32, 0, stream>>>(f->interior(), f->pitch, t, c->d_flags);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    k_wait_light<<<1, 32, 0, stream>>>(c->d_flags, mask, c->d_flags, timeout_ns, c->d_err);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    return CSIM_OK;
+}
+
+// Bootstrap record every rank contributes to the all-gather in peer_setup.
+struct PeerInfo {
+    cudaIpcMemHandle_t tile[2];
+    cudaIpcMemHandle_t flags;
+    unsigned long long raw_tile[2], raw_flags;  // same-process pointers
+    long long pid;
+    long long pitch;
+    int nx, ny, device, pad;
+};
+
+int peer_teardown(csim_ctx* c) {
+    if (!c->peer_ready && !c->d_flags) return CSIM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream_x);
+    for (auto& L : c->peer) {
+        if (L.ipc) {
+            for (double*& t : L.tile)
+                if (t) cudaIpcCloseMemHandle(t);
+            if (L.flags) cudaIpcCloseMemHandle(L.flags);
+        }
+        L = csim_ctx::PeerLink();
+    }
+    c->peer_ready = false;
+    if (c->d_flags) cudaFree(c->d_flags);
+    c->d_flags = nullptr;
+    if (c->h_err) cudaFreeHost(c->h_err);
+    c->h_err = nullptr;
+    c->d_err = nullptr;
+    return CSIM_OK;
+}
+
+// Collective over the communicator: every rank maps its neighbours' copies of (u, tmp) and their flag words.
+// Returns CSIM_OK with c->peer_ready == false (and peer_failed set) when a peer cannot be mapped; the
+// decision is agreed across ranks, so either all use the peer path or none does.
+static int peer_setup(csim_field* u, csim_field* tmp, const csim_decomp* dec) {
+    csim_ctx* c = u->ctx;
+    CSIM_CUDA(cudaSetDevice(c->device));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    if (int rc = peer_teardown(c)) return rc;
+    drop_graphs(c);  // captured block loops hold pointers into the old mappings
+    const int size = c->comm_size, me = c->comm_rank;
+    CSIM_CUDA(cudaMalloc(&c->d_flags, kCtlWords * sizeof(unsigned)));
+    CSIM_CUDA(cudaMemset(c->d_flags, 0, kCtlWords * sizeof(unsigned)));
+    CSIM_CUDA(cudaHostAlloc(&c->h_err, sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_err = 0;
+    CSIM_CUDA(cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
+    c->peer_tile[0] = u->base;
+    c->peer_tile[1] = tmp->base;
+
+    PeerInfo mine;
+    std::memset(&mine, 0, sizeof mine);
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[0], u->base));
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.tile[1], tmp->base));
+    CSIM_CUDA(cudaIpcGetMemHandle(&mine.flags, c->d_flags));
+    mine.raw_tile[0] = reinterpret_cast<unsigned long long>(u->base);
+    mine.raw_tile[1] = reinterpret_cast<unsigned long long>(tmp->base);
+    mine.raw_flags = reinterpret_cast<unsigned long long>(c->d_flags);
+    mine.pid = static_cast<long long>(getpid());
+    mine.pitch = u->pitch;
+    mine.nx = u->nx;
+    mine.ny = u->ny;
+    mine.device = c->device;
+
+    // all-gather of the records over the communicator that is already there
+    static_assert(sizeof(PeerInfo) % 8 == 0, "PeerInfo must be a whole number of doubles");
+    const size_t words = sizeof(PeerInfo) / 8;
+    double* d_all = nullptr;
+    CSIM_CUDA(cudaMalloc(&d_all, sizeof(PeerInfo) * static_cast<size_t>(size + 1)));
+    CSIM_CUDA(cudaMemcpyAsync(d_all + words * size, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    CSIM_NCCL(g_nccl.AllGather(d_all + words * size, d_all, words, ncclDouble, static_cast<ncclComm_t>(c->comm),
+                               c->stream));
+    std::vector<PeerInfo> all(static_cast<size_t>(size));
+    CSIM_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * static_cast<size_t>(size), cudaMemcpyDeviceToHost,
+                              c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaFree(d_all));
+
+    const int cx = dec->coords[0], cy = dec->coords[1];
+    double failed = 0.0;
+    int q = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            csim_ctx::PeerLink& L = c->peer[q++];
+            const int x = cx + dx, y = cy + dy;
+            if (x < 0 || y < 0 || x >= dec->dims[0] || y >= dec->dims[1]) continue;
+            const int r = x * dec->dims[1] + y;
+            CSIM_REQUIRE(r != me && r < size, CSIM_ERR_INVALID, "peer_setup: bad neighbour rank");
+            const PeerInfo& o = all[static_cast<size_t>(r)];
+            L.rank = r;
+            L.pitch = o.pitch;
+            L.nx = o.nx;
+            L.ny = o.ny;
+            if (o.pid == mine.pid) {  // ranks are threads of one process: plain peer access
+                if (o.device != c->device) {
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(o.device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled)
+                        cudaGetLastError();
+                    else if (e != cudaSuccess) {
+                        cudaGetLastError();
+                        failed = 1.0;
+                        continue;
+                    }
+                }
+                L.tile[0] = reinterpret_cast<double*>(o.raw_tile[0]);
+                L.tile[1] = reinterpret_cast<double*>(o.raw_tile[1]);
+                L.flags = reinterpret_cast<unsigned*>(o.raw_flags);
+                L.ipc = false;
+            } else {
+                void* p[3] = {nullptr, nullptr, nullptr};
+                const cudaIpcMemHandle_t* hs[3] = {&o.tile[0], &o.tile[1], &o.flags};
+                bool ok = true;
+                for (int k = 0; k < 3 && ok; ++k)
+                    if (cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                        cudaGetLastError();
+                        ok = false;
+                    }
+                L.tile[0] = static_cast<double*>(p[0]);
+                L.tile[1] = static_cast<double*>(p[1]);
+                L.flags = static_cast<unsigned*>(p[2]);
+                L.ipc = true;
+                if (!ok) failed = 1.0;
+            }
+        }
+    // agree: nobody pushes before everyone has mapped everyone (and zeroed its flags), and if any rank
+    // could not map a neighbour all ranks stay on the NCCL path
+    if (int rc = csim_comm_allreduce_max(c, &failed, 1)) return rc;
+    if (failed != 0.0) {
+        peer_teardown(c);
+        c->peer_failed = true;
+        return CSIM_OK;
+    }
+    c->peer_ready = true;
+    return CSIM_OK;
+}
+
 // ---- the block loop of csim_run_steps, its CUDA-graph replay and its timeline -----------------------
 
 // Everything a captured block loop depends on; two calls with equal keys enqueue identical work.
@@ -240,9 +598,18 @@ struct RunState {
     std::vector<RunGraph> graphs;
     uint64_t tick = 0;
     bool comm_warm = false;  // one eager pass has set up NCCL's connections to every neighbour
+    int last_path = 0;       // 0 none yet, 1 peer stores, 2 NCCL
     RunProfile prof;
     csim_halo_stats last{};
 };
+
+static void drop_graphs(csim_ctx* c) {
+    if (!c->run_state) return;
+    RunState* rs = static_cast<RunState*>(c->run_state);
+    for (RunGraph& g : rs->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    rs->graphs.clear();
+}
 
 static RunState* run_state(csim_ctx* c) {
     if (!c->run_state) c->run_state = new RunState();
@@ -278,6 +645,11 @@ static int enqueue_blocks(csim_field* u, csim_field* tmp, const csim_step_params
                           const StepK& k, int mode, int maxT, int nsteps, bool zero_terms, int values_after,
                           RunProfile* prof, int* swaps) {
     csim_ctx* c = u->ctx;
+    const bool peer = peer_tiles_match(c, u, tmp);
+    auto exchange = [&](csim_field* f, int lines, size_t* wire_out) {
+        return peer ? peer_exchange(f, dec, lines, c->stream_x, wire_out)
+                    : wide_exchange(f, dec, lines, c->stream_x, wire_out);
+    };
     int left = nsteps;
     int T = left < maxT ? left : maxT;
     *swaps = 0;
@@ -288,15 +660,18 @@ static int enqueue_blocks(csim_field* u, csim_field* tmp, const csim_step_params
     };
     CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // everything queued so far = "interior(-1)"
     CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+    if (peer)
+        if (int rc = peer_ready_barrier(c, c->stream_x)) return rc;  // the neighbours' tiles may be written now
     if (int rc = stamp(c->stream_x)) return rc;  // x0(0)
     size_t wire = 0;
-    if (int rc = wide_exchange(u, dec, T, c->stream_x, &wire)) return rc;  // exchange(0): the only one not hidden
+    if (int rc = exchange(u, T, &wire)) return rc;  // exchange(0): the only one not hidden
+    if (int rc = stamp(c->stream_x)) return rc;  // x1(0)
     if (prof) prof->bytes_per_exchange = wire;
     bool first = true;
     while (left > 0) {
         bool launched = false;
         if (!first) CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));  // interior(n-1) done
-        if (int rc = stamp(c->stream_x)) return rc;                              // x1(n) = f0(n)
+        if (int rc = stamp(c->stream_x)) return rc;                              // f0(n)
         CSIM_CUDA(cudaEventRecord(c->ev_go, c->stream_x));                       // go(n)
         if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_FRAME, c->stream_x, &launched, zero_terms)) return rc;
         CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));                     // frame(n) done
@@ -315,7 +690,8 @@ static int enqueue_blocks(csim_field* u, csim_field* tmp, const csim_step_params
         if (left > 0) {
             T = left < maxT ? left : maxT;
             if (int rc = stamp(c->stream_x)) return rc;                          // x0(n+1)
-            if (int rc = wide_exchange(u, dec, T, c->stream_x, nullptr)) return rc;  // exchange(n+1): reads frame(n)'s cells
+            if (int rc = exchange(u, T, nullptr)) return rc;  // exchange(n+1): reads frame(n)'s cells
+            if (int rc = stamp(c->stream_x)) return rc;                          // x1(n+1)
         }
     }
     CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the main stream orders everything again
@@ -330,20 +706,25 @@ static int finish_profile(csim_ctx* c, RunState* rs) {
     csim_halo_stats st{};
     st.blocks = pr.blocks;
     st.bytes_per_exchange = pr.bytes_per_exchange;
-    // event layout: base, x0(0), then per block n: x1(n) f1(n) i0(n) i1(n) [x0(n+1) unless last]
+    // event layout: base, x0(0), x1(0), then per block n: f0(n) f1(n) i0(n) i1(n) [x0(n+1) x1(n+1) unless last]
     std::vector<double> t(pr.used, 0.0);
     for (size_t i = 1; i < pr.used; ++i) {
         float ms = 0.f;
         CSIM_CUDA(cudaEventElapsedTime(&ms, pr.ev[0], pr.ev[i]));
         t[i] = ms;
     }
-    double ex = 0.0, hidden = 0.0, frame = 0.0, interior = 0.0;
+    double ex = 0.0, hidden = 0.0, frame = 0.0, interior = 0.0, gap = 0.0;
     int n_hidden = 0;
     size_t i = 1;  // t[0] is the time base
-    double x0 = t[i++];
+    double x0 = 0.0, x1 = 0.0;
+    if (pr.used >= 3) {
+        x0 = t[i];
+        x1 = t[i + 1];
+        i += 2;
+    }
     double prev_i0 = 0.0, prev_i1 = 0.0;
     for (int n = 0; n < pr.blocks && i + 3 < pr.used; ++n) {
-        const double x1 = t[i], f1 = t[i + 1], i0 = t[i + 2], i1 = t[i + 3];
+        const double f0 = t[i], f1 = t[i + 1], i0 = t[i + 2], i1 = t[i + 3];
         i += 4;
         const double dur = x1 - x0;
         if (n == 0) {
@@ -352,14 +733,20 @@ static int finish_profile(csim_ctx* c, RunState* rs) {
             ex += dur;
             const double lo = x0 > prev_i0 ? x0 : prev_i0, hi = x1 < prev_i1 ? x1 : prev_i1;
             if (hi > lo) hidden += hi - lo;
+            gap += f0 - x1;  // the frame sweep waits for the interior sweep of the previous block
             ++n_hidden;
         }
-        frame += f1 - x1;
+        frame += f1 - f0;
         interior += i1 - i0;
         prev_i0 = i0;
         prev_i1 = i1;
-        if (n + 1 < pr.blocks && i < pr.used) x0 = t[i++];
+        if (n + 1 < pr.blocks && i + 1 < pr.used) {
+            x0 = t[i];
+            x1 = t[i + 1];
+            i += 2;
+        }
     }
+    st.wait_for_interior_us = n_hidden ? 1e3 * gap / n_hidden : 0.0;
     st.exchange_us = n_hidden ? 1e3 * ex / n_hidden : st.first_exchange_us;
     st.overlap_fraction = ex > 0.0 ? hidden / ex : 0.0;
     st.frame_us = pr.blocks ? 1e3 * frame / pr.blocks : 0.0;
@@ -533,8 +920,16 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     const int values_after = zero_terms ? csim_field::kClean
                                         : (u->values == csim_field::kTainted ? csim_field::kTainted : csim_field::kUnknown);
     if (nsteps == 0) return CSIM_OK;
-    if (int rc = ensure_wide(c, u, dec, maxT)) return rc;
+    // halo path: peer stores unless refused; mapped on first use and again when the tiles change
+    if (peer_path_wanted() && !c->peer_failed && !peer_tiles_match(c, u, tmp))
+        if (int rc = peer_setup(u, tmp, dec)) return rc;
+    if (c->h_err && *c->h_err)
+        return fail(CSIM_ERR_TIMEOUT, "csim_run_steps: a neighbour's halo did not arrive within the bounded wait");
+    const bool peer = peer_tiles_match(c, u, tmp);
+    if (!peer)
+        if (int rc = ensure_wide(c, u, dec, maxT)) return rc;
     RunState* rs = run_state(c);
+    rs->last_path = peer ? 1 : 2;
     int swaps = 0;
     if (rs->prof.on) {  // profiled call: eager, with timestamps (csim_halo_profile)
         rs->prof.used = 0;
@@ -545,15 +940,19 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
         rs->comm_warm = true;
         return finish_profile(c, rs);
     }
-    // The block loop is ~8 launches per block (pack, NCCL group, unpack, frame, interior + events): at
-    // 34 blocks per 100 steps the host spent as long enqueueing them as the GPUs spent running them
-    // (round 1: 7.4 ms against 7.9 ms at 8192^2 per GPU).  So the loop is captured into a CUDA graph the
-    // first time a (tiles, parameters, step count) combination is seen and replayed afterwards; the
-    // very first call of a communicator runs eagerly, because NCCL sets up its connections to the
-    // neighbours on first use, which must not happen inside a capture.  CSIM_GRAPH=0 disables it.
+    // CUDA-graph replay of the block loop (CSIM_GRAPH=1; off by default).  With the NCCL halo path the loop
+    // is ~8 launches per block and ncclGroupEnd alone costs ~200 us of host time, so at 8192^2 per GPU the
+    // host spent as long enqueueing a window as the GPUs spent running it (round 1: 7.4 ms against 7.9 ms).
+    // Capturing the loop takes the host out (0.03 ms per window) — but the replay measured SLOWER on the
+    // device (2 x B200, 8192^2 per GPU: 8.46 ms per window against 7.42 ms eager; 16384^2: 26.9 against
+    // 26.6, profiles/r02_multigpu.md): in the graph the frame sweep and the exchange lose the stream
+    // priority that lets them overtake the interior sweep.  The peer halo path needs four small launches per
+    // block and no NCCL call, which removes the host cost without a graph; the replay stays as an option.
+    // The first call of a communicator always runs eagerly (NCCL sets up its connections on first use,
+    // which must not happen inside a capture).
     static const bool graphs_on = [] {
         const char* e = std::getenv("CSIM_GRAPH");
-        return !(e && std::strcmp(e, "0") == 0);
+        return e && std::strcmp(e, "1") == 0;
     }();
     if (!graphs_on || !rs->comm_warm) {
         if (int rc = enqueue_blocks(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, nullptr, &swaps))
@@ -568,7 +967,7 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     key.nsteps = nsteps;
     key.maxT = maxT;
     key.mode = mode;
-    key.zero_terms = zero_terms ? 1 : 0;
+    key.zero_terms = (zero_terms ? 1 : 0) | (peer ? 2 : 0);
     std::memcpy(&key.p, p, sizeof key.p);
     std::memcpy(&key.d, dec, sizeof key.d);
     ++rs->tick;
@@ -609,6 +1008,12 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     rs->graphs.push_back(g);
     CSIM_CUDA(cudaGraphLaunch(g.exec, c->stream));  // the capture recorded the work; this runs it
     return CSIM_OK;
+}
+
+const char* csim_halo_path(const csim_ctx* c) {
+    if (!c || !c->run_state) return "none";
+    const int p = static_cast<const RunState*>(c->run_state)->last_path;
+    return p == 1 ? "peer" : (p == 2 ? "nccl" : "none");
 }
 
 int csim_halo_profile(csim_ctx* c, int enable) {

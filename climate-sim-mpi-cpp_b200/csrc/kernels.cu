@@ -736,6 +736,9 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
 }
 
 int csim_steps_per_sweep(void) { return tb_max_T(); }
+const char* csim_sweep_kernel(void) {
+    return tb_staged_enabled() && tb_has_staged_variant(tb_max_T(), MODE_UNIT) ? "k_step_tbs" : "k_step_tb";
+}
 
 int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps, int part,
                     csim_sweep_item* items, int capacity, int* count) {

@@ -75,6 +75,8 @@ public:
     // device side (used by the step functions)
     csim_field* device_ro() const;  // tile with current contents, for reading
     csim_field* device_rw();        // same, and marks the device copy as the newer one
+    csim_field* device_overwrite(); // the tile WITHOUT its current contents (the caller rewrites every cell):
+                                    // no upload of a newer host copy; marks the device copy as the newer one
     void fill_device(double v);     // Field::fill without touching the host copy
 
 private:

@@ -5,9 +5,12 @@
 // csim_dropin.hpp.
 #include "csim_dropin.hpp"
 
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cerrno>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -53,7 +56,11 @@ csim_ctx* default_context() {
         int dev = env_int("CSIM_DEVICE", nullptr, -1);
         if (dev < 0) {
             const int local = env_int("CSIM_LOCAL_RANK", "LOCAL_RANK", world().rank);
-            dev = local;  // one rank per GPU of the box, GPU id = rank
+            int ndev = 0;
+            if (csim_device_count(&ndev) != CSIM_OK) ndev = 0;
+            // one rank per GPU of the box, GPU id = rank; with more ranks than GPUs the
+            // ranks share them round-robin
+            dev = ndev > 0 ? local % ndev : local;
         }
         check(csim_ctx_create(dev, &g_ctx));
     });
@@ -139,6 +146,13 @@ csim_field* MirroredData::device_rw() {
     st_->dev_newer = true;
     return st_->dev;
 }
+csim_field* MirroredData::device_overwrite() {
+    State& s = *st_;
+    if (!s.dev) check(csim_field_create(default_context(), s.nx, s.ny, s.h, s.dx, s.dy, &s.dev));
+    s.host_newer = false;
+    s.dev_newer = true;
+    return s.dev;
+}
 void MirroredData::fill_device(double v) {
     State& s = *st_;
     if (!s.dev) check(csim_field_create(default_context(), s.nx, s.ny, s.h, s.dx, s.dy, &s.dev));
@@ -210,7 +224,12 @@ void Decomp2D::finalize() { cart_comm = MPI_COMM_NULL; }
 
 // ---- step functions ------------------------------------------------------------------------------
 void diffusion_step(const Field& u, Field& out, double D, double dt) {
-    check(csim_diffusion_step(u.data.device_ro(), out.data.device_rw(), D, dt));
+    // with halo 1 the interior update plus the ring copy (diffusion.cpp:9-25) rewrite every cell of `out`,
+    // so a newer host copy of `out` (main.cpp:104's std::copy leaves one) need not travel to the device
+    const bool rewrites_all = out.halo == 1 && u.halo == 1 && out.nx_local == u.nx_local &&
+                              out.ny_local == u.ny_local && u.nx_local > 0 && u.ny_local > 0 && &u != &out;
+    check(csim_diffusion_step(u.data.device_ro(), rewrites_all ? out.data.device_overwrite() : out.data.device_rw(), D,
+                              dt));
 }
 void advection_step(const Field& u, Field& out, double vx, double vy, double dt) {
     check(csim_advection_step(u.data.device_ro(), out.data.device_rw(), vx, vy, dt));
@@ -245,8 +264,10 @@ void run_timesteps(Field& u, Field& tmp, const Decomp2D& dec, const BCConfig& bc
     for (int s = 0; s < 4; ++s) p.nbr[s] = c.nbr[s];
     p.bc_value = 0.0;  // src/main.cpp:102
     p.flags = 0;
+    if (nsteps <= 0) return;
     csim_field* du = u.data.device_rw();
-    csim_field* dt_ = tmp.data.device_rw();
+    // tmp is scratch: every step rewrites it from u (main.cpp:104), so its host copy never needs uploading
+    csim_field* dt_ = tmp.data.device_overwrite();
     // more than one rank: halos travel as packed T-line bands over grouped NCCL send/recv
     // csim_run_steps swaps the device buffers of the two tiles an odd or even number of times; the
     // newest state ends up in u's handle either way.
@@ -279,11 +300,32 @@ double MPI_Wtime(void) {
 }
 
 // Rendezvous of the NCCL id through a file: rank 0 writes it atomically, the others poll.
+// The file lives under $XDG_RUNTIME_DIR when there is one (else /tmp), carries the user id and a job
+// token in its name, and starts with a magic word and the same token, so that a file left behind by a
+// crashed run or planted by someone else is not mistaken for this job's: CSIM_JOB_ID (any string the
+// launcher gives every rank) or, without it, the parent process id (ranks started by one launcher share it).
+static std::string job_token() {
+    if (const char* j = std::getenv("CSIM_JOB_ID")) return j;
+    if (const char* j = std::getenv("TORCHELASTIC_RUN_ID")) return j;
+    return std::to_string(static_cast<long long>(getppid()));
+}
 static std::string rendezvous_path() {
     if (const char* p = std::getenv("CSIM_RENDEZVOUS")) return p;
+    const char* dir = std::getenv("XDG_RUNTIME_DIR");
     const char* port = std::getenv("MASTER_PORT");
-    return std::string("/tmp/csim_rendezvous_") + (port ? port : "default");
+    std::string tok = job_token();
+    for (char& ch : tok)
+        if (!std::isalnum(static_cast<unsigned char>(ch))) ch = '_';
+    return std::string(dir && *dir ? dir : "/tmp") + "/csim_rendezvous_" + std::to_string(static_cast<long long>(getuid())) +
+           "_" + (port ? port : "default") + "_" + tok;
 }
+namespace {
+struct RendezvousRecord {
+    char magic[8];
+    char token[56];
+    char id[CSIM_UNIQUE_ID_BYTES];
+};
+}  // namespace
 
 int MPI_Init(int*, char***) {
     auto& w = csim_host::world();
@@ -291,28 +333,41 @@ int MPI_Init(int*, char***) {
     w.initialized = true;
     if (w.size <= 1) return MPI_SUCCESS;
     csim_ctx* ctx = csim_host::default_context();
-    char id[CSIM_UNIQUE_ID_BYTES];
+    RendezvousRecord rec;
+    std::memset(&rec, 0, sizeof rec);
+    std::memcpy(rec.magic, "CSIMRDV1", 8);
+    std::strncpy(rec.token, job_token().c_str(), sizeof rec.token - 1);
     const std::string path = rendezvous_path();
     if (w.rank == 0) {
-        check(csim_comm_unique_id(id));
+        check(csim_comm_unique_id(rec.id));
         const std::string tmp = path + ".tmp";
-        {
-            std::ofstream o(tmp, std::ios::binary | std::ios::trunc);
-            o.write(id, sizeof id);
-        }
-        std::rename(tmp.c_str(), path.c_str());
+        ::unlink(tmp.c_str());
+        ::unlink(path.c_str());  // a stale record of an earlier run must not be read as ours
+        const int fd = ::open(tmp.c_str(), O_CREAT | O_EXCL | O_NOFOLLOW | O_WRONLY, 0600);
+        if (fd < 0) throw std::runtime_error("MPI_Init (csim shim): cannot create " + tmp + ": " + std::strerror(errno));
+        const bool ok = ::write(fd, &rec, sizeof rec) == static_cast<ssize_t>(sizeof rec);
+        ::close(fd);
+        if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0)
+            throw std::runtime_error("MPI_Init (csim shim): cannot publish " + path);
     } else {
         bool got = false;
+        RendezvousRecord in_rec;
         for (int tries = 0; tries < 1200 && !got; ++tries) {  // up to 60 s
-            std::ifstream in(path, std::ios::binary);
-            if (in && in.read(id, sizeof id)) got = true;
+            const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+            if (fd >= 0) {
+                const bool whole = ::read(fd, &in_rec, sizeof in_rec) == static_cast<ssize_t>(sizeof in_rec);
+                ::close(fd);
+                got = whole && std::memcmp(in_rec.magic, rec.magic, 8) == 0 &&
+                      std::memcmp(in_rec.token, rec.token, sizeof rec.token) == 0;
+            }
             if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(50));
         }
-        if (!got) throw std::runtime_error("MPI_Init (csim shim): no rendezvous file " + path);
+        if (!got) throw std::runtime_error("MPI_Init (csim shim): no rendezvous record for this job at " + path);
+        std::memcpy(rec.id, in_rec.id, sizeof rec.id);
     }
-    check(csim_comm_init(ctx, w.size, w.rank, id));
+    check(csim_comm_init(ctx, w.size, w.rank, rec.id));
     check(csim_comm_allreduce_max(ctx, nullptr, 0));  // barrier: everyone has read the id
-    if (w.rank == 0) std::remove(path.c_str());
+    if (w.rank == 0) ::unlink(path.c_str());
     return MPI_SUCCESS;
 }
 int MPI_Init_thread(int* argc, char*** argv, int required, int* provided) {

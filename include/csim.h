@@ -43,7 +43,7 @@ typedef enum csim_status {
     CSIM_ERR_RANGE = 4,       /* index outside the padded tile (Field::at → std::out_of_range) */
     CSIM_ERR_UNSUPPORTED = 5, /* valid in the reference, not on this path (e.g. halo != 1)     */
     CSIM_ERR_COMM = 6,        /* NCCL failure                                                  */
-    CSIM_ERR_TIMEOUT = 7      /* reserved (was: bounded wait of the removed peer-push halo)    */
+    CSIM_ERR_TIMEOUT = 7      /* a neighbour's halo did not arrive within the bounded wait     */
 } csim_status;
 
 /* enum class BCType { Dirichlet, Neumann, Periodic } — reference include/boundary.hpp:5 */
@@ -63,6 +63,8 @@ typedef struct csim_field csim_field; /* one halo-padded, pitch-aligned device t
 /* Bind a context to CUDA device `device` and create its stream. */
 int csim_ctx_create(int device, csim_ctx** out);
 int csim_ctx_destroy(csim_ctx* ctx);
+/* Number of CUDA devices visible to the process (0 with CSIM_ERR_CUDA when there is none). */
+int csim_device_count(int* count);
 /* MPI_Barrier / end-of-loop ordering of src/main.cpp:82,120: wait for all queued work. */
 int csim_sync(csim_ctx* ctx);
 /* cudaStream_t of the context as an opaque pointer (for CUDA-event timing by the caller). */
@@ -100,6 +102,10 @@ int csim_field_download(const csim_field* f, double* host_padded);
 /* The de-haloed tile, ny*nx doubles — the buffer src/io.cpp:411-416 assembles before its put.
  * `host_dense` should be pinned for full PCIe speed; csim_host_alloc provides that. */
 int csim_field_download_interior(const csim_field* f, double* host_dense);
+/* A w x h window of the tile, first cell (x0, y0) in INTERIOR coordinates (ghost cells are -1 and nx / ny),
+ * into a dense host array of h rows of w doubles; synchronous.  For spot checks of tiles too large to
+ * bring back whole.  CSIM_ERR_RANGE if the window leaves the padded tile. */
+int csim_field_download_window(const csim_field* f, int x0, int y0, int w, int h, double* host_dense);
 /* Same, asynchronous on the context stream (host buffer must be pinned; order with csim_sync). */
 int csim_field_upload_async(csim_field* f, const double* host_padded_pinned);
 int csim_field_download_interior_async(const csim_field* f, double* host_dense_pinned);
@@ -186,6 +192,9 @@ typedef struct csim_step_params {
 int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, int nsteps);
 /* Largest number of time steps one sweep advances (the temporal blocking depth T; env CSIM_TB_MAXT). */
 int csim_steps_per_sweep(void);
+/* Name of the sweep kernel that depth runs with unit spacing: "k_step_tbs" (level-0 rows staged through
+ * shared memory by TMA; the default) or "k_step_tb" (register-only; CSIM_TB_KERNEL=reg).  For reports. */
+const char* csim_sweep_kernel(void);
 
 /* min / max over the whole padded tile, ghosts included — the "IC min/max" reduction of
  * src/main.cpp:73-77 (std::min_element / std::max_element over Field::data). */
@@ -238,6 +247,14 @@ int csim_comm_allreduce_max(csim_ctx* ctx, double* inout, int n);
  * over NVLink, and unpacked by a kernel; all on the context stream. */
 int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
 
+/* Which halo path csim_run_steps used last on this context: "none" (no neighbours yet), "peer" (the
+ * T-line bands are stored straight into the neighbours' ghost lines over NVLink by single-warp CTAs that
+ * co-reside with the interior sweep, one flag per neighbour; tiles mapped with CUDA IPC between processes,
+ * peer access inside one) or "nccl" (pack kernel, grouped ncclSend/ncclRecv, unpack kernel: CSIM_HALO=nccl,
+ * or peers that cannot be mapped).  The peer path is set up on first use — collectively: every rank's
+ * first csim_run_steps with a given pair of tiles must be the same call. */
+const char* csim_halo_path(const csim_ctx* ctx);
+
 /* One region of the wide (T-line, 8-neighbour) exchange csim_run_steps performs per T-step block:
  * interior coordinates of its first cell, extent, and the rank on the other side (-1: no such
  * neighbour).  Index k enumerates directions (dx,dy) row by row from (-1,-1) to (1,1) without (0,0). */
@@ -287,6 +304,8 @@ typedef struct csim_halo_stats {
     double frame_us;           /* mean frame sweep (edge strips + first/last chunks: the ghost-line readers) */
     double interior_us;        /* mean interior sweep                                                   */
     double total_ms;           /* first to last timestamp of the call                                   */
+    double wait_for_interior_us; /* mean time between the end of an exchange and the start of its frame sweep:
+                                  the exchange stream waiting for the previous block's interior sweep  */
 } csim_halo_stats;
 int csim_halo_profile(csim_ctx* ctx, int enable);
 int csim_halo_stats_get(csim_ctx* ctx, csim_halo_stats* out);

@@ -300,6 +300,56 @@ def test_full_size_windows_and_linearity(csim, ctx, oracle_mod, port, n):
     assert np.all(u.download_interior() == 3.141592653589793)
 
 
+def _window_oracle(csim, oracle_mod, port, nxg, nyg, gx, gy, w, steps, phys, bc):
+    """Oracle field of the w x w window at global (gx, gy) after `steps` time steps from the Gaussian initial
+    condition: the sub-domain reaches `steps` cells beyond the window (its dependency cone) or to the physical
+    boundary; cut sides carry the neighbouring cells' initial values as frozen ghosts."""
+    y0, y1 = max(gy - steps, 0), min(gy + w + steps, nyg)
+    x0, x1 = max(gx - steps, 0), min(gx + w + steps, nxg)
+    sub = np.zeros((y1 - y0 + 2, x1 - x0 + 2))
+    iy0, iy1, ix0, ix1 = max(y0 - 1, 0), min(y1 + 1, nyg), max(x0 - 1, 0), min(x1 + 1, nxg)
+    sub[iy0 - (y0 - 1):iy1 - (y0 - 1), ix0 - (x0 - 1):ix1 - (x0 - 1)] = csim.initial_condition_host(
+        csim.Decomp2D.window(nxg, nyg, ix0, iy0, ix1 - ix0, iy1 - iy0), 0, 1.0, 1.0)
+    cut = (bc[0] if x0 == 0 else 2, bc[1] if x1 == nxg else 2, bc[2] if y0 == 0 else 2, bc[3] if y1 == nyg else 2)
+    sp = oracle_mod.SimParams(nx=x1 - x0, ny=y1 - y0, steps=steps, out_every=steps, bc=cut, **phys)
+    return port.run(sp, u0_padded=sub)["final"][gy - y0:gy - y0 + w, gx - x0:gx - x0 + w]
+
+
+@pytest.mark.parametrize("n,bc", [(16384, (2, 2, 2, 2)), (32768, (0, 1, 0, 1))])
+def test_north_star_tiles_100_steps_against_oracle_windows(csim, ctx, oracle_mod, port, n, bc):
+    """configs[2]'s 16384^2 tile (all-periodic) and configs[3]'s 32768^2 grid with Dirichlet left/bottom and
+    Neumann right/top on ONE GPU (2 x 8.6 GB), 100 time steps — a whole output window: 25 four-step sweeps,
+    or 33 + a remainder sweep — for the headline physics (vy = 0: the dropped-term kernel) and the all-terms
+    physics.  The initial condition is generated on the device where the host libm allows (else uploaded),
+    the oracle runs on the sub-domain around each of 11 windows (four corners, four edge midpoints, centre,
+    two interior points), and the windows come back with csim_field_download_window."""
+    steps, w = 100, 48
+    dec = csim.Decomp2D.single(n, n)
+    B = csim.BCType
+    u = csim.Field(ctx, n, n, 1, 1.0, 1.0)
+    tmp = csim.Field(ctx, n, n, 1, 1.0, 1.0)
+    pts = [(0, 0), (0, n - w), (n - w, 0), (n - w, n - w), (0, n // 2), (n - w, n // 2 - 7), (n // 2, 0),
+           (n // 3, n - w), (n // 2 - w // 2, n // 2 - w // 2), (1234, 4321), (3 * n // 4, n // 3 + 5)]
+    try:
+        for phys in (dict(D=0.05, vx=0.5, vy=0.0, dt=0.1), dict(D=0.05, vx=-0.5, vy=0.25, dt=0.1)):
+            if csim.exp_variant() >= 0:
+                u.fill(0.0)
+                csim.initial_condition_device(u, dec)
+            else:
+                u.upload(csim.initial_condition_host(dec, 1, 1.0, 1.0))
+            p = csim.make_step_params(phys["D"], phys["vx"], phys["vy"], phys["dt"], csim.BCConfig(*[B(b) for b in bc]),
+                                      dec)
+            csim.run_steps(u, tmp, p, dec, steps)
+            if phys["vy"] == 0.0:
+                assert u.value_state == 1  # the scan found the tile clean: the dropped-term kernel ran
+            for (y, x) in pts:
+                want = _window_oracle(csim, oracle_mod, port, n, n, x, y, w, steps, phys, bc)
+                assert bits_equal(u.download_window(x, y, w, w), want), (n, phys, y, x)
+    finally:
+        u.close()
+        tmp.close()
+
+
 # ---- dropped zero-velocity terms (csim_field_value_state, DESIGN.md) ------------------------------
 
 def plateau_tile(rng, ny, nx, negzero=False):
@@ -509,9 +559,12 @@ def test_cpp_dropin_unit_tests():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
 
 
-def test_multi_process_parity_under_torchrun():
-    """One PROCESS per GPU under torchrun (how bench.py runs), with the CUDA-graph replay of the block
-    loop on and off."""
+@pytest.mark.parametrize("env,path", [({}, "peer"), ({"CSIM_HALO": "nccl"}, "nccl"), ({"CSIM_GRAPH": "1"}, "peer"),
+                                      ({"CSIM_HALO": "nccl", "CSIM_GRAPH": "1"}, "nccl")])
+def test_multi_process_parity_under_torchrun(env, path):
+    """One PROCESS per GPU under torchrun (how bench.py runs): the peer halo path maps the neighbours' tiles
+    with CUDA IPC here, which the threaded test above cannot exercise; also the NCCL path, and both with the
+    block loop replayed as a CUDA graph."""
     import os
     import subprocess
     import sys
@@ -523,8 +576,11 @@ def test_multi_process_parity_under_torchrun():
     world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mp_parity_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=e)
     assert r.returncode == 0 and "MP_PARITY_PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"halo={path}" in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("env", [{"CSIM_TB_MAXT": "4"}, {"CSIM_TB_MAXT": "2"}, {"CSIM_TB_MAXT": "1"},
