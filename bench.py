@@ -369,9 +369,16 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count - l0
         barrier()
+        per_rank.clear()
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device="cuda")
+            t[rank] = ms
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank.extend(float(v) for v in t.tolist())
         return reduce_max(ms), reduce_sum_int(launches)
 
     enqueue_s = []
+    per_rank = []  # device time of the last timed() region on every rank
 
     def window_resident():
         t0 = time.perf_counter()
@@ -382,6 +389,7 @@ def run_ours(args):
     sampler.start()
     ms, launches = timed(window_resident, args.steps, args.warmup)
     clocks = sampler.stop()
+    ms_per_rank = [v / args.steps for v in per_rank]
     # dev.yaml has vy = 0, so on the (clean, monotone) benchmark field the library drops the y-advection
     # term: 11 instead of 14 FP64 operations per cell (csim_field_value_state).  Time the same window
     # with both velocity components non-zero and negative vx as well, so the full arithmetic and the
@@ -428,6 +436,7 @@ def run_ours(args):
             "overlap_fraction": -reduce_max(-st["overlap_fraction"]),  # the worst rank
             "us_frame_sweep": reduce_max(st["frame_us"]), "us_interior_sweep": reduce_max(st["interior_us"]),
             "us_exchange_done_to_frame_start": reduce_max(st["wait_for_interior_us"]),
+            "us_own_store_kernel": reduce_max(st["push_us"]) if csim.halo_path(ctx) == "peer" else None,
             "path": csim.halo_path(ctx),
             "note": "one exchange = everything between the end of the frame sweep and the start of the next one on the "
                     "exchange stream (peer: store kernel + flag wait; nccl: pack + grouped send/recv + unpack), CUDA "
@@ -615,6 +624,7 @@ def run_ours(args):
                           "note": "same windows with both velocity components non-zero (14 FP64 ops per cell): the "
                                   "rate of a run whose velocity has no exact zero component"},
             "gpu_launches": launches, "clocks": clocks,
+            "ms_per_step_per_rank": ms_per_rank or None,
             "host_enqueue_ms_per_step": 1e3 * float(np.median(enqueue_s[-args.steps:])) if enqueue_s else None,
         }
         print(json.dumps(line), flush=True)

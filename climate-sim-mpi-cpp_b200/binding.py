@@ -75,7 +75,8 @@ class HaloStats(C.Structure):
     """csim_halo_stats"""
     _fields_ = [("blocks", C.c_int), ("bytes_per_exchange", C.c_size_t), ("first_exchange_us", C.c_double),
                 ("exchange_us", C.c_double), ("overlap_fraction", C.c_double), ("frame_us", C.c_double),
-                ("interior_us", C.c_double), ("total_ms", C.c_double), ("wait_for_interior_us", C.c_double)]
+                ("interior_us", C.c_double), ("total_ms", C.c_double), ("push_us", C.c_double),
+                ("wait_for_interior_us", C.c_double)]
 
 
 class StepParams(C.Structure):

@@ -223,18 +223,43 @@ enum { kCtlTicket = 8, kCtlPushSeq = 9, kCtlWaitSeq = 10, kCtlReadySeq = 11, kCt
 // Store all regions into the neighbours' tiles; the last CTA to finish (ticket) publishes the sequence
 // number of this push in every neighbour's flag word.  The sequence number lives in device memory so
 // that a CUDA-graph replay pushes the right one.
-__global__ void __maxnreg__(32) k_push_light(const double* __restrict__ u, long long pitch,
-                                                                   PushTable t, unsigned* __restrict__ ctl) {
+// The work is cut into chunks of 32 x kPushBatch cells across all eight regions, and a warp keeps a whole
+// chunk in flight: kPushBatch independent loads per lane, then as many remote stores.  With one load and
+// one store at a time (the first version) every cell paid a full round trip through a memory system that
+// the interior sweep keeps saturated: 1.4 GB/s, 1.1 ms per exchange on 8 GPUs (profiles/r02_multigpu.md).
+constexpr int kPushBatch = 8;
+__global__ void __maxnreg__(32) k_push_light(const double* __restrict__ u, long long pitch, PushTable t,
+                                             unsigned* __restrict__ ctl) {
     const int lane = threadIdx.x;
+    constexpr int kChunk = 32 * kPushBatch;
+    int chunk0 = 0;  // first global chunk id of region q
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
         const PushRegion g = t.r[q];
         if (!g.flag) continue;
         const int n = g.w * g.h;
-        for (int e = blockIdx.x * 32 + lane; e < n; e += gridDim.x * 32) {
-            const int yy = e / g.w, xx = e - yy * g.w;
-            g.dst[static_cast<long long>(yy) * g.dst_pitch + xx] = u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx];
+        const int nchunks = (n + kChunk - 1) / kChunk;
+        // chunks are dealt round-robin over the CTAs, continuing across regions
+        int first = static_cast<int>(blockIdx.x) - chunk0 % static_cast<int>(gridDim.x);
+        if (first < 0) first += gridDim.x;
+#pragma unroll 1
+        for (int ch = first; ch < nchunks; ch += gridDim.x) {
+            const int e0 = ch * kChunk + lane;
+            double v[kPushBatch];
+#pragma unroll
+            for (int k = 0; k < kPushBatch; ++k) {
+                const int e = e0 + 32 * k;
+                const int yy = e / g.w, xx = e - yy * g.w;
+                v[k] = e < n ? u[static_cast<long long>(g.y0 + yy) * pitch + g.x0 + xx] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < kPushBatch; ++k) {
+                const int e = e0 + 32 * k;
+                const int yy = e / g.w, xx = e - yy * g.w;
+                if (e < n) g.dst[static_cast<long long>(yy) * g.dst_pitch + xx] = v[k];
+            }
         }
+        chunk0 += nchunks;
     }
     __threadfence_system();  // this thread's peer stores are visible system-wide before the ticket
     __syncwarp();
@@ -347,12 +372,36 @@ static int peer_ready_barrier(csim_ctx* c, cudaStream_t stream) {
     return CSIM_OK;
 }
 
+// CSIM_HALO=peer opts into the peer-store path; the default is the NCCL path, which holds ~100 % weak-scaling
+// efficiency at 8 GPUs where the peer path, better at 2 GPUs, collapses (profiles/r02_multigpu.md).
 static bool peer_path_wanted() {
-    static const bool nccl_only = [] {
+    static const bool peer = [] {
         const char* e = std::getenv("CSIM_HALO");
-        return e && std::strcmp(e, "nccl") == 0;
+        return e && (std::strcmp(e, "peer") == 0 || std::strcmp(e, "p2p") == 0);
     }();
-    return !nccl_only;
+    return peer;
+}
+// CSIM_CARVEOUT=<percent>: pin the shared-memory carve-out of the light kernels (and, in kernels.cu, of the
+// staged sweep) to the same value — a measurement aid for the question whether kernels with different
+// carve-outs can share an SM.
+static int light_carveout() {
+    static const int v = [] {
+        const char* e = std::getenv("CSIM_CARVEOUT");
+        return e ? std::atoi(e) : -1;
+    }();
+    return v;
+}
+static void light_prepare() {
+    static const bool done = [] {
+        const int pct = light_carveout();
+        if (pct >= 0) {
+            cudaFuncSetAttribute(k_push_light, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_wait_light, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_ready_light, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        return true;
+    }();
+    (void)done;
 }
 static bool peer_tiles_match(const csim_ctx* c, const csim_field* u, const csim_field* tmp) {
     return c->peer_ready && ((u->base == c->peer_tile[0] && tmp->base == c->peer_tile[1]) ||
@@ -364,8 +413,10 @@ static bool peer_tiles_match(const csim_ctx* c, const csim_field* u, const csim_
 // stores into ours.  Double buffering makes the remote stores safe: exchange(n+1) writes the buffer whose
 // ghost lines the neighbour last read in frame(n-1), and we only get here after the neighbour's push(n),
 // which it queued behind its frame(n-1).
-static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream, size_t* bytes_sent) {
+static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStream_t stream, size_t* bytes_sent,
+                         cudaEvent_t after_push = nullptr) {
     csim_ctx* c = f->ctx;
+    light_prepare();
     csim_decomp d = *dec;
     d.nx_local = f->nx;
     d.ny_local = f->ny;
@@ -411,6 +462,7 @@ static int peer_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     k_push_light<<<c->sm_count, 32, 0, stream>>>(f->interior(), f->pitch, t, c->d_flags);
     ++c->launches;
     CSIM_CUDA(cudaGetLastError());
+    if (after_push) CSIM_CUDA(cudaEventRecord(after_push, stream));
     k_wait_light<<<1, 32, 0, stream>>>(c->d_flags, mask, c->d_flags, timeout_ns, c->d_err);
     ++c->launches;
     CSIM_CUDA(cudaGetLastError());
@@ -579,7 +631,8 @@ struct RunGraph {
 // frame sweep on the exchange stream and around the interior sweep on the main stream.
 struct RunProfile {
     bool on = false;
-    std::vector<cudaEvent_t> ev;  // base, then 6 per block: x0 x1 f1 i0 i1 (f0 == x1) + spare
+    std::vector<cudaEvent_t> ev;  // base, x0(0) x1(0), then per block f0 f1 i0 i1 [x0 x1]
+    std::vector<cudaEvent_t> mid; // peer path: one per exchange, recorded between the push and the wait kernel
     size_t used = 0;
     int blocks = 0;
     size_t bytes_per_exchange = 0;
@@ -647,8 +700,14 @@ static int enqueue_blocks(csim_field* u, csim_field* tmp, const csim_step_params
     csim_ctx* c = u->ctx;
     const bool peer = peer_tiles_match(c, u, tmp);
     auto exchange = [&](csim_field* f, int lines, size_t* wire_out) {
-        return peer ? peer_exchange(f, dec, lines, c->stream_x, wire_out)
-                    : wide_exchange(f, dec, lines, c->stream_x, wire_out);
+        if (!peer) return wide_exchange(f, dec, lines, c->stream_x, wire_out);
+        cudaEvent_t mid = nullptr;
+        if (prof) {  // push | wait split of the exchange, kept apart from the main timeline
+            cudaSetDevice(c->device);
+            cudaEventCreate(&mid);
+            prof->mid.push_back(mid);
+        }
+        return peer_exchange(f, dec, lines, c->stream_x, wire_out, mid);
     };
     int left = nsteps;
     int T = left < maxT ? left : maxT;
@@ -747,6 +806,25 @@ static int finish_profile(csim_ctx* c, RunState* rs) {
         }
     }
     st.wait_for_interior_us = n_hidden ? 1e3 * gap / n_hidden : 0.0;
+    // peer path: how much of an exchange is this rank's own store kernel (the rest is waiting for the neighbours')
+    st.push_us = 0.0;
+    if (pr.mid.size() > 1) {
+        // exchange k (k >= 1) starts at the x0 recorded right before it: events 1 (k = 0), then 7 + 6 (k - 1)
+        double sum = 0.0;
+        int cnt = 0;
+        for (size_t k = 1; k < pr.mid.size(); ++k) {
+            const size_t ix0 = 7 + 6 * (k - 1);
+            if (ix0 >= pr.used) break;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.ev[ix0], pr.mid[k]) == cudaSuccess) {
+                sum += ms;
+                ++cnt;
+            }
+        }
+        st.push_us = cnt ? 1e3 * sum / cnt : 0.0;
+    }
+    for (cudaEvent_t e : pr.mid) cudaEventDestroy(e);
+    pr.mid.clear();
     st.exchange_us = n_hidden ? 1e3 * ex / n_hidden : st.first_exchange_us;
     st.overlap_fraction = ex > 0.0 ? hidden / ex : 0.0;
     st.frame_us = pr.blocks ? 1e3 * frame / pr.blocks : 0.0;
@@ -934,6 +1012,8 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
     if (rs->prof.on) {  // profiled call: eager, with timestamps (csim_halo_profile)
         rs->prof.used = 0;
         rs->prof.blocks = 0;
+        for (cudaEvent_t e : rs->prof.mid) cudaEventDestroy(e);
+        rs->prof.mid.clear();
         CSIM_CUDA(cudaEventRecord(rs->prof.next(c), c->stream));  // time base
         if (int rc = enqueue_blocks(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, &rs->prof, &swaps))
             return rc;

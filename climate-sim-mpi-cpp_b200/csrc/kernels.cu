@@ -352,6 +352,10 @@ static int tb_env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
 }
+int tb_carveout_env() {
+    static const int v = tb_env_int("CSIM_CARVEOUT", -1);
+    return v;
+}
 // Blocking depth with IEEE division (non-power-of-two spacing).  The divisions make the sweep
 // compute-bound already at one step per sweep, so blocking in time only adds the re-computed halo
 // cells; measured in profiles/r02_tuning.md.  CSIM_TB_DIV_MAXT = 2 or 3 opts in.

@@ -13,6 +13,8 @@ namespace csim {
 // staged = false: k_step_tb  (level-0 rows loaded into registers one tick ahead),
 // staged = true : k_step_tbs (level-0 rows landed in a shared-memory ring by TMA; exists for T >= 3 in the
 //                 multiplication modes, which is where the loop spends its time)
+int tb_carveout_env();  // kernels.cu: CSIM_CARVEOUT (percent) or -1
+
 template <int VXS, int VYS>
 cudaError_t tb_launch_signed(bool staged, int T, int mode, const TbArgs& a, cudaStream_t stream) {
     const dim3 block(32 * kTbWarpsPerBlock);
@@ -24,6 +26,14 @@ cudaError_t tb_launch_signed(bool staged, int T, int mode, const TbArgs& a, cuda
     }
 #define CSIM_TBS_CASE(TT, MM)                                                 \
     if (staged && T == TT && mode == MM) {                                    \
+        static const bool prepared = [] {                                     \
+            const int pct = tb_carveout_env();                                \
+            if (pct >= 0)                                                     \
+                cudaFuncSetAttribute(k_step_tbs<TT, MM, VXS, VYS>,            \
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct); \
+            return true;                                                      \
+        }();                                                                  \
+        (void)prepared;                                                       \
         k_step_tbs<TT, MM, VXS, VYS><<<grid, block, 0, stream>>>(a);          \
         return cudaGetLastError();                                            \
     }

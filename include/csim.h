@@ -304,6 +304,7 @@ typedef struct csim_halo_stats {
     double frame_us;           /* mean frame sweep (edge strips + first/last chunks: the ghost-line readers) */
     double interior_us;        /* mean interior sweep                                                   */
     double total_ms;           /* first to last timestamp of the call                                   */
+    double push_us;            /* peer path: this rank's own store kernel, start of the exchange to its end (0: NCCL path) */
     double wait_for_interior_us; /* mean time between the end of an exchange and the start of its frame sweep:
                                   the exchange stream waiting for the previous block's interior sweep  */
 } csim_halo_stats;

@@ -559,12 +559,12 @@ def test_cpp_dropin_unit_tests():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("env,path", [({}, "peer"), ({"CSIM_HALO": "nccl"}, "nccl"), ({"CSIM_GRAPH": "1"}, "peer"),
-                                      ({"CSIM_HALO": "nccl", "CSIM_GRAPH": "1"}, "nccl")])
+@pytest.mark.parametrize("env,path", [({}, "nccl"), ({"CSIM_HALO": "peer"}, "peer"), ({"CSIM_GRAPH": "1"}, "nccl"),
+                                      ({"CSIM_HALO": "peer", "CSIM_GRAPH": "1"}, "peer")])
 def test_multi_process_parity_under_torchrun(env, path):
-    """One PROCESS per GPU under torchrun (how bench.py runs): the peer halo path maps the neighbours' tiles
-    with CUDA IPC here, which the threaded test above cannot exercise; also the NCCL path, and both with the
-    block loop replayed as a CUDA graph."""
+    """One PROCESS per GPU under torchrun (how bench.py runs): the default NCCL halo path and the peer-store
+    path (CSIM_HALO=peer), which maps the neighbours' tiles with CUDA IPC here — the threaded test above
+    cannot exercise that — and both with the block loop replayed as a CUDA graph."""
     import os
     import subprocess
     import sys
