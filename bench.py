@@ -478,6 +478,19 @@ def run_ours(args):
             ctx.sync()
 
         ms_serial, _ = timed(window_copies, 2, 1)
+
+        # what the box gives a bare device→host copy of one frame when every rank copies at once: the ceiling
+        # of the per-window time above once the sweeps (shorter) are hidden behind the copy
+        def bare_copy():
+            ctx.event_wait(u.snapshot_async(host_out[0]))
+
+        bare_copy()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bare_copy()
+        copy_s = reduce_max((time.perf_counter() - t0) / 3)
+        barrier()
         cells_w = float(nxg) * float(nyg) * inner
         e2e = {"value": cells_w * e2e_steps / secs, "unit": "cell-updates/s",
                "h2d_bytes_per_step": int(host_in.nbytes // e2e_steps), "d2h_bytes_per_step": int(host_out[0].nbytes),
@@ -487,6 +500,10 @@ def run_ours(args):
                        "h2d_bytes_per_step), then per window 100 time steps + D2H of the de-haloed tile on the copy "
                        "stream, overlapping the next window's steps (what src/main.cpp:93-99 does at output steps); "
                        "host wall clock around a full drain, max over ranks",
+               "d2h_copy_alone": {"ms_per_frame": 1e3 * copy_s, "gbs_per_rank": host_out[0].nbytes / copy_s / 1e9,
+                                  "gbs_all_ranks": world * host_out[0].nbytes / copy_s / 1e9,
+                                  "note": "pack + PCIe copy of one de-haloed frame with no time steps queued, all ranks "
+                                          "at once, max over ranks: what a window costs when the copy is the bound"},
                "per_window_copies": {"value": cells_w * 2 / (ms_serial * 1e-3), "ms_per_step": ms_serial / 2,
                                      "h2d_bytes_per_step": int(host_in.nbytes), "d2h_bytes_per_step": int(host_out[0].nbytes),
                                      "mode": "every window: H2D of the padded tile, 100 steps, D2H, sync — no overlap"}}

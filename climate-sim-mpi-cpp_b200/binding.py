@@ -185,6 +185,11 @@ def lib():
         L.csim_safe_dt.restype = C.c_double
         L.csim_abi_version.restype = C.c_int
         L.csim_steps_per_sweep.restype = C.c_int
+        if hasattr(L, "csim_div_by_const"):
+            L.csim_div_by_const.argtypes = [C.c_double, C.c_double]
+            L.csim_div_by_const.restype = C.c_double
+            L.csim_div_by_const_fast.argtypes = [C.c_double, C.c_double]
+            L.csim_div_by_const_fast.restype = C.c_int
         if hasattr(L, "csim_sweep_kernel"):
             L.csim_sweep_kernel.restype = C.c_char_p
         if hasattr(L, "csim_halo_path"):
@@ -535,6 +540,15 @@ def initial_condition_device(f: "Field", dec: Decomp2D, preset="gaussian_hotspot
         raise RuntimeError("Unknown IC preset: " + preset)  # init.cpp:42
     _check(lib().csim_initial_condition_device(f._h, C.byref(dec._c), dec.nx_global, dec.ny_global,
                                                presets[preset], A, sigma_frac, xc_frac, yc_frac))
+
+
+def div_by_const(a: float, d: float) -> float:
+    """The kernels' constant-divisor division (step_math.cuh) on the host."""
+    return float(lib().csim_div_by_const(a, d))
+
+
+def div_by_const_fast(a: float, d: float) -> bool:
+    return bool(lib().csim_div_by_const_fast(a, d))
 
 
 def sweep_kernel() -> str:

@@ -192,3 +192,4 @@ extern "C" int csim_bind_thread_to_device_numa(int device, int* node) {
     if (sched_setaffinity(0, sizeof set, &set) == 0 && node) *node = n;
     return CSIM_OK;
 }
+

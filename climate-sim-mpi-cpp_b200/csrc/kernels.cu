@@ -739,6 +739,10 @@ int csim_step_fused(csim_field* u, csim_field* tmp, const csim_step_params* p, i
     return CSIM_OK;
 }
 
+// The kernels' division by a constant divisor, run on the host (same source, step_math.cuh) — for tests.
+double csim_div_by_const(double a, double d) { return div_by_const(a, d, 1.0 / d); }
+int csim_div_by_const_fast(double a, double d) { return div_by_const_took_fast_path(a, d); }
+
 int csim_steps_per_sweep(void) { return tb_max_T(); }
 const char* csim_sweep_kernel(void) {
     return tb_staged_enabled() && tb_has_staged_variant(tb_max_T(), MODE_UNIT) ? "k_step_tbs" : "k_step_tb";

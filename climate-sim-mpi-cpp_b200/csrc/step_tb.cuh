@@ -39,6 +39,9 @@ constexpr int kTbWarpsPerBlock = 4;
 constexpr int kTbBlocksPerSM = 3;                  // 168 registers per thread, 12 warps per SM
 
 enum { MODE_UNIT = 0, MODE_RECIP = 1, MODE_DIV = 2 };
+// internal to the row routines: MODE_DIV's divisions by the checked reciprocal sequence (step_math.cuh), the
+// verdict of the checks AND-ed into tb_update's `ok`; a row whose checks did not all pass is redone in MODE_DIV_IEEE
+enum { MODE_DIV_IEEE = 3 };
 
 struct TbArgs {
     const double* u;   // level-0 field, pointer to interior cell (0,0)
@@ -102,7 +105,8 @@ __host__ __device__ __forceinline__ bool tb_item_map(const TbArgs& a, int item, 
 // creates a -0 where there was none.  The dispatcher (kernels.cu, zero_terms_allowed) uses the 0
 // variants only for fields it has scanned (finite, no -0, on every rank) and a stable time step.
 template <int MODE, int VXS, int VYS>
-__device__ __forceinline__ double tb_update(double c, double w, double e, double s, double n, const StepK& k) {
+__device__ __forceinline__ double tb_update(double c, double w, double e, double s, double n, const StepK& k,
+                                            bool& ok) {
     // e - 2.0*c and n - 2.0*c as one FMA each: 2.0*c is exact (a power-of-two scaling), so
     // fma(-2, c, e) rounds the same real number as the reference's (e - 2.0*c) — one rounding either
     // way — as long as 2|c| does not overflow (|c| < 2^1023; csim_field_health reports max|u|).
@@ -113,6 +117,11 @@ __device__ __forceinline__ double tb_update(double c, double w, double e, double
         lx = __dmul_rn(lx, k.rdx2);
         ly = __dmul_rn(ly, k.rdy2);
     } else if (MODE == MODE_DIV) {
+        bool o1, o2;
+        lx = div_by_const_try(lx, k.dx2, k.rdx2, o1);
+        ly = div_by_const_try(ly, k.dy2, k.rdy2, o2);
+        ok = ok && o1 && o2;
+    } else if (MODE == MODE_DIV_IEEE) {
         lx = __ddiv_rn(lx, k.dx2);
         ly = __ddiv_rn(ly, k.dy2);
     }
@@ -122,13 +131,23 @@ __device__ __forceinline__ double tb_update(double c, double w, double e, double
     if (VXS != 0) {
         double ddx = VXS > 0 ? __dsub_rn(c, w) : __dsub_rn(e, c);
         if (MODE == MODE_RECIP) ddx = __dmul_rn(ddx, k.rdx);
-        if (MODE == MODE_DIV) ddx = __ddiv_rn(ddx, k.dx);
+        if (MODE == MODE_DIV) {
+            bool o;
+            ddx = div_by_const_try(ddx, k.dx, k.rdx, o);
+            ok = ok && o;
+        }
+        if (MODE == MODE_DIV_IEEE) ddx = __ddiv_rn(ddx, k.dx);
         px = __dmul_rn(k.vx, ddx);
     }
     if (VYS != 0) {
         double ddy = VYS > 0 ? __dsub_rn(c, s) : __dsub_rn(n, c);
         if (MODE == MODE_RECIP) ddy = __dmul_rn(ddy, k.rdy);
-        if (MODE == MODE_DIV) ddy = __ddiv_rn(ddy, k.dy);
+        if (MODE == MODE_DIV) {
+            bool o;
+            ddy = div_by_const_try(ddy, k.dy, k.rdy, o);
+            ok = ok && o;
+        }
+        if (MODE == MODE_DIV_IEEE) ddy = __ddiv_rn(ddy, k.dy);
         py = __dmul_rn(k.vy, ddy);
     }
     const double adv = VXS == 0 ? py : (VYS == 0 ? px : __dadd_rn(px, py));
@@ -167,10 +186,17 @@ __device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j,
     const double e3 = __shfl_down_sync(0xffffffffu, c[0], 1);
     if (KIND != TICK_GEN) {
         double r[4];
-        r[0] = tb_update<MODE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k);
-        r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k);
-        r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k);
-        r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k);
+        bool ok = true;
+        r[0] = tb_update<MODE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k, ok);
+        r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k, ok);
+        r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k, ok);
+        r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k, ok);
+        if (MODE == MODE_DIV && __any_sync(0xffffffffu, !ok)) {  // rare: a quotient the check could not prove
+            r[0] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[0], w0, c[1], s[0], n[0], a.k, ok);
+            r[1] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[1], c[0], c[2], s[1], n[1], a.k, ok);
+            r[2] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[2], c[1], c[3], s[2], n[2], a.k, ok);
+            r[3] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[3], c[2], e3, s[3], n[3], a.k, ok);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) res[i] = (KIND == TICK_FAST || ((ln.inx >> i) & 1)) ? r[i] : c[i];
         return;
@@ -217,10 +243,17 @@ __device__ __forceinline__ void tb_row(const TbArgs& a, const TbLane& ln, int j,
         if (i == ln.ghost_r) keep[i] = bc_pick(a.bcR, a.value, i == 0 ? w0 : c[i == 0 ? 0 : i - 1], c[i]);  // x == nx
     }
     double r[4];
-    r[0] = tb_update<MODE, VXS, VYS>(c[0], ww0, ee[0], ss[0], nn[0], a.k);
-    r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], ee[1], ss[1], nn[1], a.k);
-    r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], ee[2], ss[2], nn[2], a.k);
-    r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], ee[3], ss[3], nn[3], a.k);
+    bool ok = true;
+    r[0] = tb_update<MODE, VXS, VYS>(c[0], ww0, ee[0], ss[0], nn[0], a.k, ok);
+    r[1] = tb_update<MODE, VXS, VYS>(c[1], c[0], ee[1], ss[1], nn[1], a.k, ok);
+    r[2] = tb_update<MODE, VXS, VYS>(c[2], c[1], ee[2], ss[2], nn[2], a.k, ok);
+    r[3] = tb_update<MODE, VXS, VYS>(c[3], c[2], ee[3], ss[3], nn[3], a.k, ok);
+    if (MODE == MODE_DIV && __any_sync(0xffffffffu, !ok)) {
+        r[0] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[0], ww0, ee[0], ss[0], nn[0], a.k, ok);
+        r[1] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[1], c[0], ee[1], ss[1], nn[1], a.k, ok);
+        r[2] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[2], c[1], ee[2], ss[2], nn[2], a.k, ok);
+        r[3] = tb_update<MODE_DIV_IEEE, VXS, VYS>(c[3], c[2], ee[3], ss[3], nn[3], a.k, ok);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) res[i] = ((ln.inx >> i) & 1) ? r[i] : keep[i];
 }

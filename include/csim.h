@@ -328,6 +328,11 @@ int csim_initial_condition_host(double* host_padded, const csim_decomp* dec, int
 int csim_initial_condition_device(csim_field* f, const csim_decomp* dec, int nx_global, int ny_global,
                                   int preset, double A, double sigma_frac, double xc_frac, double yc_frac);
 int csim_exp_variant(void);
+/* The kernels' division by a divisor known in advance (csrc/step_math.cuh: reciprocal, one correction step,
+ * an exact check, IEEE division as the fallback) executed on the host, and whether (a, d) passes the check —
+ * for tests against true division.  d must be positive, finite and normal. */
+double csim_div_by_const(double a, double d);
+int csim_div_by_const_fast(double a, double d);
 /* The restated exp() itself on the host (variant 1 or 0), for tests against the host libm. */
 double csim_exp_restated(double x, int variant);
 
