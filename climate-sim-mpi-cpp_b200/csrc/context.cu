@@ -162,6 +162,8 @@ int csim_ctx_destroy(csim_ctx* c) {
         if (c->ev_snap_done[b]) cudaEventDestroy(c->ev_snap_done[b]);
         if (c->d_snapbuf[b]) cudaFree(c->d_snapbuf[b]);
     }
+    if (c->d_couple) cudaFree(c->d_couple);
+    if (c->h_couple_err) cudaFreeHost(c->h_couple_err);
     if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_wide) cudaFree(c->d_wide);
     if (c->d_snap) cudaFree(c->d_snap);
@@ -176,7 +178,7 @@ int csim_sync(csim_ctx* c) {
     CSIM_CUDA(cudaStreamSynchronize(c->stream));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
     CSIM_CUDA(cudaStreamSynchronize(c->stream_copy));
-    if (c->h_err && *c->h_err)
+    if ((c->h_err && *c->h_err) || (c->h_couple_err && *c->h_couple_err))
         return fail(CSIM_ERR_TIMEOUT, "csim_sync: a neighbour's halo did not arrive within the bounded wait");
     return CSIM_OK;
 }

@@ -64,6 +64,10 @@ struct csim_ctx {
     cudaEvent_t ev_snap_packed[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
     int snap_next = 0;
     bool exp_table_loaded = false;    // initcond.cu: 2^(k/128) table copied to this device
+    unsigned* d_couple = nullptr;     // halo.cu: [0] halo landed, [1] frame done, [2] ticket (coupled block loop)
+    unsigned* h_couple_err = nullptr; // pinned, mapped: set before a coupled wait traps
+    unsigned* d_couple_err = nullptr;
+    unsigned couple_seq = 0;
     void* run_state = nullptr;        // halo.cu: captured block loops (CUDA graphs) and the halo timeline
     cudaStream_t stream_x = nullptr;  // exchange + frame sweep, overlapped with the interior sweep
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_go = nullptr;
@@ -101,7 +105,7 @@ bool is_pow2(double x);
 void run_state_destroy(csim_ctx* c);  // halo.cu
 int peer_teardown(csim_ctx* c);        // halo.cu
 struct StepK;
-enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2 };
+enum { TB_ALL = 0, TB_INTERIOR = 1, TB_FRAME = 2, TB_COUPLED = 3 };
 int tb_max_T();
 int tb_max_T_div();
 bool tb_split_pointless(int nchunks, int n_int);
@@ -111,8 +115,18 @@ int step_setup(const csim_field* u, const csim_step_params* p, StepK* k, int* mo
 // Scans `u` if its state is unknown (one pass + host sync, once per upload).
 int resolve_zero_terms(csim_field* u, const csim_step_params* p, const StepK& k, int mode, int maxT,
                        bool* allowed);
+// Coupling of a TB_COUPLED launch with the exchange stream (step_tb.cuh: tb_frame_enter / tb_frame_leave)
+struct TbCoupling {
+    unsigned seq = 0;
+    unsigned* halo_flag = nullptr;
+    unsigned* done_flag = nullptr;
+    unsigned* ticket = nullptr;
+    unsigned* err = nullptr;
+    unsigned long long timeout_ns = 0;
+};
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms = false);
+                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms = false,
+                   const TbCoupling* coupling = nullptr);
 
 }  // namespace csim
 

@@ -679,6 +679,145 @@ void run_state_destroy(csim_ctx* c) {
     c->run_state = nullptr;
 }
 
+// ---- the coupled block loop: ONE sweep launch per block, flags instead of stream events -------------
+// Main stream   : sweep(0), sweep(1), … back to back.  In sweep(n) the frame items (the ones that read ghost
+//                 lines) come first; each checks `halo landed >= n` before it requests a row (normally true
+//                 long before the launch), and the last one to finish sets `frame done = n`.
+// Exchange stream: wait(frame done >= n) → exchange(n+1) → set(halo landed = n+1), all while sweep(n)'s
+//                 interior items run.  The wait and set kernels are single-warp CTAs that fit beside a full
+//                 sweep; the exchange itself has a whole sweep of slack (≈ 1 ms at 16384^2).
+// Against the split loop below (frame and interior as two launches on two streams, ordered by events) this
+// removes the two cross-stream hops every block start paid for — interior(n) done → frame(n+1) may start →
+// interior(n+1) may start — which cost 3–4.5 % at 2 and 4 GPUs (profiles/r02_multigpu.md), and it no longer
+// matters when NCCL's kernel finds room on the SMs.
+__global__ void __maxnreg__(32) k_flag_wait_light(const unsigned* flag, unsigned seq, unsigned long long timeout_ns,
+                                                  unsigned* err) {
+    if (threadIdx.x == 0) {
+        const volatile unsigned* f = flag;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (static_cast<int>(*f - seq) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                *reinterpret_cast<volatile unsigned*>(err) = 202u;
+                __threadfence_system();
+                __trap();
+            }
+            __nanosleep(200);
+        }
+        __threadfence();
+    }
+}
+__global__ void __maxnreg__(32) k_flag_set_light(unsigned* flag, unsigned seq) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(flag) = seq;
+    }
+}
+
+static int ensure_coupling(csim_ctx* c) {
+    if (c->d_couple) return CSIM_OK;
+    CSIM_CUDA(cudaMalloc(&c->d_couple, 8 * sizeof(unsigned)));
+    CSIM_CUDA(cudaMemset(c->d_couple, 0, 8 * sizeof(unsigned)));
+    CSIM_CUDA(cudaHostAlloc(&c->h_couple_err, sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_couple_err = 0;
+    CSIM_CUDA(cudaHostGetDevicePointer(&c->d_couple_err, c->h_couple_err, 0));
+    c->couple_seq = 0;
+    // Load the two flag kernels NOW.  With lazy module loading the first launch of a function can wait for
+    // the device to go idle; a sweep whose frame items spin until k_flag_wait_light → exchange → k_flag_set_light
+    // have run would then wait for a kernel that cannot be loaded while it spins (observed: both ranks
+    // trapped on the 60 s bound the first time the wait kernel was launched behind a dependent sweep).
+    cudaFuncAttributes fa;
+    CSIM_CUDA(cudaFuncGetAttributes(&fa, k_flag_wait_light));
+    CSIM_CUDA(cudaFuncGetAttributes(&fa, k_flag_set_light));
+    k_flag_set_light<<<1, 32, 0, c->stream_x>>>(c->d_couple + 1, 0u);
+    k_flag_wait_light<<<1, 32, 0, c->stream_x>>>(c->d_couple + 1, 0u, 1000000000ull, c->d_couple_err);
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    return CSIM_OK;
+}
+
+static int enqueue_blocks_coupled(csim_field* u, csim_field* tmp, const csim_step_params* p, const csim_decomp* dec,
+                                  const StepK& k, int mode, int maxT, int nsteps, bool zero_terms, int values_after,
+                                  RunProfile* prof, int* swaps) {
+    csim_ctx* c = u->ctx;
+    if (int rc = ensure_coupling(c)) return rc;
+    const bool peer = peer_tiles_match(c, u, tmp);
+    auto exchange = [&](csim_field* f, int lines, size_t* wire_out) {
+        return peer ? peer_exchange(f, dec, lines, c->stream_x, wire_out)
+                    : wide_exchange(f, dec, lines, c->stream_x, wire_out);
+    };
+    auto stamp = [&](cudaStream_t st) -> int {
+        if (!prof) return CSIM_OK;
+        CSIM_CUDA(cudaEventRecord(prof->next(c), st));
+        return CSIM_OK;
+    };
+    TbCoupling cp;
+    cp.halo_flag = c->d_couple + 0;
+    cp.done_flag = c->d_couple + 1;
+    cp.ticket = c->d_couple + 2;
+    cp.err = c->d_couple_err;
+    cp.timeout_ns = peer_timeout_ns();
+    int left = nsteps;
+    int T = left < maxT ? left : maxT;
+    *swaps = 0;
+    CSIM_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // everything queued on the tiles so far
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_fork, 0));
+    if (peer)
+        if (int rc = peer_ready_barrier(c, c->stream_x)) return rc;
+    if (int rc = stamp(c->stream_x)) return rc;  // x0(0)
+    size_t wire = 0;
+    if (int rc = exchange(u, T, &wire)) return rc;  // exchange(0): the only one not hidden
+    if (prof) prof->bytes_per_exchange = wire;
+    unsigned seq = ++c->couple_seq;
+    k_flag_set_light<<<1, 32, 0, c->stream_x>>>(cp.halo_flag, seq);
+    ++c->launches;
+    CSIM_CUDA(cudaGetLastError());
+    if (int rc = stamp(c->stream_x)) return rc;  // x1(0)
+    // Host order: sweep(n+1) is queued on the main stream BEFORE the exchange stream gets the work of
+    // exchange(n+1).  The two only meet through the flags, so the order is free on the host — and NCCL's
+    // enqueue can block the host until the device has taken earlier operations of the communicator, which
+    // here wait for sweep(n)'s frame items: queued the other way round, every sweep launch arrived late
+    // (measured: host enqueue time = device time, 65 us of idle GPU per block at 16384^2).
+    bool launched = false;
+    cp.seq = seq;
+    if (int rc = stamp(c->stream)) return rc;  // s0(0)
+    if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_COUPLED, c->stream, &launched, zero_terms, &cp)) return rc;
+    if (int rc = stamp(c->stream)) return rc;  // s1(0)
+    tmp->values = values_after;
+    csim_field_swap(u, tmp);  // u: the state after block 0 (being computed)
+    ++*swaps;
+    if (prof) ++prof->blocks;
+    left -= T;
+    while (left > 0) {
+        const unsigned seq_done = seq;  // frame items of the sweep in flight publish this
+        T = left < maxT ? left : maxT;
+        seq = ++c->couple_seq;
+        cp.seq = seq;
+        if (int rc = stamp(c->stream)) return rc;  // s0(n+1)
+        if (int rc = launch_step_tb(u, tmp, p, k, mode, T, TB_COUPLED, c->stream, &launched, zero_terms, &cp)) return rc;
+        if (int rc = stamp(c->stream)) return rc;  // s1(n+1)
+        // exchange(n+1) on the state sweep(n) is writing (u): its bands are final once sweep(n)'s frame items are done
+        k_flag_wait_light<<<1, 32, 0, c->stream_x>>>(cp.done_flag, seq_done, cp.timeout_ns, cp.err);
+        ++c->launches;
+        CSIM_CUDA(cudaGetLastError());
+        if (int rc = stamp(c->stream_x)) return rc;  // x0(n+1)
+        if (int rc = exchange(u, T, nullptr)) return rc;
+        k_flag_set_light<<<1, 32, 0, c->stream_x>>>(cp.halo_flag, seq);
+        ++c->launches;
+        CSIM_CUDA(cudaGetLastError());
+        if (int rc = stamp(c->stream_x)) return rc;  // x1(n+1)
+        tmp->values = values_after;
+        csim_field_swap(u, tmp);
+        ++*swaps;
+        if (prof) ++prof->blocks;
+        left -= T;
+    }
+    // whatever follows on the main stream is ordered after the exchange stream as well
+    CSIM_CUDA(cudaEventRecord(c->ev_join, c->stream_x));
+    CSIM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    return CSIM_OK;
+}
+
 // Software pipeline over blocks of T steps, two streams:
 //   exchange stream (high priority): go(n) → frame(n) → exchange(n+1)
 //   main stream                    : wait go(n) → interior(n)
@@ -830,6 +969,56 @@ static int finish_profile(csim_ctx* c, RunState* rs) {
     st.frame_us = pr.blocks ? 1e3 * frame / pr.blocks : 0.0;
     st.interior_us = pr.blocks ? 1e3 * interior / pr.blocks : 0.0;
     st.total_ms = pr.used ? t[pr.used - 1] : 0.0;
+    rs->last = st;
+    pr.on = false;
+    return CSIM_OK;
+}
+
+// Timeline of a profiled coupled call: base, x0(0), x1(0), then per block s0(n) s1(n) [x0(n+1) x1(n+1)].
+static int finish_profile_coupled(csim_ctx* c, RunState* rs) {
+    RunProfile& pr = rs->prof;
+    CSIM_CUDA(cudaStreamSynchronize(c->stream));
+    CSIM_CUDA(cudaStreamSynchronize(c->stream_x));
+    csim_halo_stats st{};
+    st.blocks = pr.blocks;
+    st.bytes_per_exchange = pr.bytes_per_exchange;
+    std::vector<double> t(pr.used, 0.0);
+    for (size_t i = 1; i < pr.used; ++i) {
+        float ms = 0.f;
+        CSIM_CUDA(cudaEventElapsedTime(&ms, pr.ev[0], pr.ev[i]));
+        t[i] = ms;
+    }
+    double ex = 0.0, hidden = 0.0, sweep = 0.0;
+    int n_ex = 0;
+    if (pr.used >= 3) st.first_exchange_us = 1e3 * (t[2] - t[1]);
+    // events: base, x0(0), x1(0), s0(0), s1(0), then for every further block m: s0(m) s1(m) x0(m) x1(m);
+    // exchange(m) runs beside sweep(m-1)
+    size_t i = 3;
+    double prev_s0 = 0.0, prev_s1 = 0.0;
+    for (int m = 0; m < pr.blocks && i + 1 < pr.used; ++m) {
+        const double s0 = t[i], s1 = t[i + 1];
+        i += 2;
+        sweep += s1 - s0;
+        if (m > 0 && i + 1 < pr.used) {
+            const double x0 = t[i], x1 = t[i + 1];
+            i += 2;
+            ex += x1 - x0;
+            const double lo = x0 > prev_s0 ? x0 : prev_s0, hi = x1 < prev_s1 ? x1 : prev_s1;
+            if (hi > lo) hidden += hi - lo;
+            ++n_ex;
+        }
+        prev_s0 = s0;
+        prev_s1 = s1;
+    }
+    st.exchange_us = n_ex ? 1e3 * ex / n_ex : st.first_exchange_us;
+    st.overlap_fraction = ex > 0.0 ? hidden / ex : 0.0;
+    st.frame_us = 0.0;  // frame and interior items share one launch
+    st.interior_us = pr.blocks ? 1e3 * sweep / pr.blocks : 0.0;
+    st.total_ms = pr.used ? t[pr.used - 1] : 0.0;
+    st.push_us = 0.0;
+    st.wait_for_interior_us = 0.0;
+    for (cudaEvent_t e : pr.mid) cudaEventDestroy(e);
+    pr.mid.clear();
     rs->last = st;
     pr.on = false;
     return CSIM_OK;
@@ -1008,6 +1197,27 @@ int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p, co
         if (int rc = ensure_wide(c, u, dec, maxT)) return rc;
     RunState* rs = run_state(c);
     rs->last_path = peer ? 1 : 2;
+    // CSIM_LOOP=coupled: one sweep launch per block, coupled to the exchange stream by flags; default
+    // (CSIM_LOOP=split): frame and interior as two launches on two streams, ordered by events
+    static const bool coupled = [] {
+        const char* e = std::getenv("CSIM_LOOP");
+        return e && std::strcmp(e, "coupled") == 0;
+    }();
+    if (c->h_couple_err && *c->h_couple_err)
+        return fail(CSIM_ERR_TIMEOUT, "csim_run_steps: a halo or frame flag did not arrive within the bounded wait");
+    if (coupled) {
+        int swaps_c = 0;
+        RunProfile* pf = rs->prof.on ? &rs->prof : nullptr;
+        if (pf) {
+            pf->used = 0;
+            pf->blocks = 0;
+            CSIM_CUDA(cudaEventRecord(pf->next(c), c->stream));  // time base
+        }
+        if (int rc = enqueue_blocks_coupled(u, tmp, p, dec, k, mode, maxT, nsteps, zero_terms, values_after, pf, &swaps_c))
+            return rc;
+        rs->comm_warm = true;
+        return pf ? finish_profile_coupled(c, rs) : CSIM_OK;
+    }
     int swaps = 0;
     if (rs->prof.on) {  // profiled call: eager, with timestamps (csim_halo_profile)
         rs->prof.used = 0;

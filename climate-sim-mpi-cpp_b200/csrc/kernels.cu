@@ -537,6 +537,7 @@ static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int sl
     }
     a.int_chunk0 = 0;
     a.frame_pair = 0;
+    a.n_frame_items = a.n_frame_tickets = a.n_frame_edge_items = 0;
     int int_chunks = a.nchunks;
     a.n_edge_items = n_edge * nch_edge;
     // The interior part may run while the halos travel, so none of its items may read a ghost line:
@@ -562,13 +563,28 @@ static bool tb_geometry(int nx, int ny, long long pitch, int T, int phys, int sl
             int_chunks = a.nchunks;
         }
     }
+    else if (part == TB_COUPLED) {  // the frame's items first, then the interior's, in one launch
+        a.frame_pair = split_ok ? 1 : 0;
+        a.n_frame_edge_items = a.n_edge_items;
+        const int frame_int = split_ok ? 2 : a.nchunks;
+        a.n_frame_items = a.n_edge_items + n_int * frame_int;
+        const int interior_chunks = split_ok ? a.nchunks - 2 : 0;
+        a.n_items = a.n_frame_items + n_int * interior_chunks;
+        int tickets = 0;
+        for (int item = 0; item < a.n_frame_items; ++item) {
+            int strip, ya, yb;
+            if (tb_item_map(a, item, strip, ya, yb)) ++tickets;
+        }
+        a.n_frame_tickets = tickets;
+        return a.n_items > 0;
+    }
     if (int_chunks < 0) int_chunks = 0;
     a.n_items = n_int * int_chunks + a.n_edge_items;
     return a.n_items > 0;
 }
 
 int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params* p, const StepK& k, int mode,
-                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms) {
+                   int T, int part, cudaStream_t stream, bool* launched, bool zero_terms, const TbCoupling* coupling) {
     csim_ctx* c = u->ctx;
     TbArgs a;
     a.u = u->interior();
@@ -580,6 +596,19 @@ int launch_step_tb(const csim_field* u, csim_field* out, const csim_step_params*
     if (launched) *launched = false;
     const int slots = c->sm_count * kTbBlocksPerSM * kTbWarpsPerBlock;
     if (!tb_geometry(u->nx, u->ny, u->pitch, T, phys, slots, part, a)) return CSIM_OK;
+    if (part == TB_COUPLED) {
+        CSIM_REQUIRE(coupling != nullptr, CSIM_ERR_INVALID, "launch_step_tb: coupled launch without coupling");
+        a.seq = coupling->seq;
+        a.halo_flag = coupling->halo_flag;
+        a.done_flag = coupling->done_flag;
+        a.ticket = coupling->ticket;
+        a.err = coupling->err;
+        a.timeout_ns = coupling->timeout_ns;
+    } else {
+        a.seq = 0;
+        a.halo_flag = a.done_flag = a.ticket = a.err = nullptr;
+        a.timeout_ns = 0;
+    }
     a.bcL = p->bc[0];
     a.bcR = p->bc[1];
     a.bcB = p->bc[2];
@@ -752,7 +781,7 @@ int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps,
                     csim_sweep_item* items, int capacity, int* count) {
     CSIM_REQUIRE(nbr != nullptr && count != nullptr && (items != nullptr || capacity == 0), CSIM_ERR_INVALID,
                  "csim_sweep_plan: null argument");
-    CSIM_REQUIRE(nx >= 1 && ny >= 1 && T >= 1 && T <= kTbMaxT && part >= TB_ALL && part <= TB_FRAME, CSIM_ERR_INVALID,
+    CSIM_REQUIRE(nx >= 1 && ny >= 1 && T >= 1 && T <= kTbMaxT && part >= TB_ALL && part <= TB_COUPLED, CSIM_ERR_INVALID,
                  "csim_sweep_plan: bad size, depth or part");
     int phys = 0;
     for (int s = 0; s < 4; ++s)

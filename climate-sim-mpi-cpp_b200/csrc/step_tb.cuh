@@ -65,6 +65,17 @@ struct TbArgs {
     int xmax_load;     // a lane may load its 4 cells iff x0+3 < xmax_load (row allocation bound)
     int pf_rows;       // L2 prefetch distance in rows (off: a huge distance, which no row guard passes)
     long long pf_off;  // pf_rows * pitch
+    // coupled launch of the multi-GPU loop (part TB_COUPLED): the frame items come first, [0, n_frame_items),
+    // wait for the halo of this block before they read a ghost line and count a ticket down when they are done
+    int n_frame_items;      // 0: no coupling (every other part)
+    int n_frame_tickets;    // frame items that have rows (the ones that will take a ticket)
+    int n_frame_edge_items; // of the frame items, how many belong to the edge strips
+    unsigned seq;           // this block's sequence number
+    unsigned* halo_flag;    // >= seq once the exchange of this block has landed in the ghost lines
+    unsigned* done_flag;    // set to seq by the last frame item to finish: the bands of the next exchange are final
+    unsigned* ticket;
+    unsigned* err;
+    unsigned long long timeout_ns;
     int phys;          // bit s: side s (left,right,bottom,top) is a physical boundary
     int bcL, bcR, bcB, bcT;
     double value;      // Dirichlet value
@@ -76,25 +87,69 @@ struct TbArgs {
 // chunk_h rows (chunk_h2 in the tail of the launch); the slower edge strips get edge_split times as
 // many chunks of chunk_h/edge_split rows and are enumerated first so that they never form the tail.
 // Returns false for an item without rows.
-__host__ __device__ __forceinline__ bool tb_item_map(const TbArgs& a, int item, int& strip, int& ya, int& yb) {
+__host__ __device__ __forceinline__ bool tb_item_decode(const TbArgs& a, int item, int n_edge_items, int int_chunk0,
+                                                        int frame_pair, int& strip, int& ya, int& yb) {
     const int n_edge = a.nstrips >= 2 ? 2 : 1;
     const int n_int = a.nstrips - n_edge;
     int h;
-    if (item < a.n_edge_items) {
+    if (item < n_edge_items) {
         strip = (item % n_edge) ? a.nstrips - 1 : 0;
         h = (a.chunk_h + a.edge_split - 1) / a.edge_split;
         ya = a.sy0 + (item / n_edge) * h;
     } else {
-        const int e = item - a.n_edge_items;
+        const int e = item - n_edge_items;
         strip = 1 + e % n_int;
         const int ci = e / n_int;
-        const int chunk = a.frame_pair ? (ci ? a.nchunks - 1 : 0) : a.int_chunk0 + ci;
+        const int chunk = frame_pair ? (ci ? a.nchunks - 1 : 0) : int_chunk0 + ci;
         const bool tail = chunk >= a.n_main;
         h = tail ? a.chunk_h2 : a.chunk_h;
         ya = a.sy0 + (tail ? a.n_main * a.chunk_h + (chunk - a.n_main) * a.chunk_h2 : chunk * a.chunk_h);
     }
     yb = ya + h < a.sy1 ? ya + h : a.sy1;
     return ya < a.sy1;
+}
+__host__ __device__ __forceinline__ bool tb_item_map(const TbArgs& a, int item, int& strip, int& ya, int& yb) {
+    if (a.n_frame_items > 0) {  // coupled launch: the frame's items in the frame's order, then the interior's
+        if (item < a.n_frame_items)
+            return tb_item_decode(a, item, a.n_frame_edge_items, 0, a.frame_pair, strip, ya, yb);
+        return tb_item_decode(a, item - a.n_frame_items, 0, 1, 0, strip, ya, yb);
+    }
+    return tb_item_decode(a, item, a.n_edge_items, a.int_chunk0, a.frame_pair, strip, ya, yb);
+}
+
+// Coupled launches: a frame item may not read a ghost line before the exchange of this block has landed
+// (flag written on the exchange stream, normally long before the launch), and the last frame item to finish
+// releases the next exchange.  Both are warp-uniform and outside every loop.
+__device__ __forceinline__ void tb_frame_enter(const TbArgs& a, int item, int lane) {
+    if (item >= a.n_frame_items) return;
+    if (lane == 0) {
+        const volatile unsigned* f = a.halo_flag;
+        if (static_cast<int>(*f - a.seq) < 0) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (static_cast<int>(*f - a.seq) < 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > a.timeout_ns) {
+                    *reinterpret_cast<volatile unsigned*>(a.err) = 201u;
+                    __threadfence_system();
+                    __trap();
+                }
+                __nanosleep(200);
+            }
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void tb_frame_leave(const TbArgs& a, int item, int lane) {
+    if (item >= a.n_frame_items) return;
+    __threadfence();  // this item's cells are visible device-wide before its ticket
+    __syncwarp();
+    if (lane == 0 && atomicAdd(a.ticket, 1u) == static_cast<unsigned>(a.n_frame_tickets) - 1u) {
+        *a.ticket = 0;  // re-armed for the next block (launches of one stream do not overlap)
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(a.done_flag) = a.seq;
+    }
 }
 
 // One cell update.  VXS / VYS select the upwind side: +1 for v >= 0 (backward difference), -1 for
@@ -372,6 +427,7 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
 
     int strip, ya, yb;
     if (!tb_item_map(a, item, strip, ya, yb)) return;
+    tb_frame_enter(a, item, lane);
     const int xb = strip * kTbWout - kTbHX;
     TbLane ln;
     ln.x0 = xb + lane * kTbCells;
@@ -442,6 +498,7 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
             r += 4;
         }
     }
+    tb_frame_leave(a, item, lane);
 }
 
 }  // namespace csim

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
 
     int strip, ya, yb;
     if (!tb_item_map(a, item, strip, ya, yb)) return;
+    tb_frame_enter(a, item, lane);  // coupled launches: no ghost line is requested before its halo has landed
     const int xb = strip * kTbWout - kTbHX;
     TbLane ln;
     ln.x0 = xb + lane * kTbCells;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(32 * kTbWarpsPerBlock, kTbBlocksPerSM) k_step_
             r += 4;
         }
     }
+    tb_frame_leave(a, item, lane);
 }
 
 }  // namespace csim

@@ -269,7 +269,7 @@ int csim_wide_exchange_plan(const csim_decomp* dec, int T, csim_xregion send[8],
 
 /* Host-only: the work items one fused sweep of T steps is cut into on a tile of nx x ny cells whose
  * sides with nbr[s] == CSIM_PROC_NULL are physical, for a machine with `resident_warps` warp slots
- * (0: 148 SMs x 12).  part: 0 the whole sweep, 1 the items that read no ghost line (overlapped with the
+ * (0: 148 SMs x 12).  part: 0 the whole sweep, 3 the same items with the frame's first (one coupled launch), 1 the items that read no ghost line (overlapped with the
  * halo exchange), 2 the others (the frame).  Each item is one warp's job: the rows [y0, y1) of the
  * finished columns [x0, x1) of strip `strip` (interior coordinates; ghost lines of physical sides are
  * -1 and nx / ny).  Writes at most `capacity` items and returns the total number in *count.  Lets the

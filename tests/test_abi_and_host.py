@@ -129,6 +129,8 @@ def test_sweep_plan_tiles_the_stored_region_exactly_once(csim, nx, ny):
                 inner = csim.sweep_plan(nx, ny, T, nbr, slots, 1)
                 frame = csim.sweep_plan(nx, ny, T, nbr, slots, 2)
                 assert sorted(inner + frame) == sorted(whole), (T, nbr, slots)
+                # the coupled launch of the multi-GPU loop: the frame's items first, then the interior's
+                assert csim.sweep_plan(nx, ny, T, nbr, slots, 3) == frame + inner, (T, nbr, slots)
                 # interior items never touch the first/last chunk of a strip nor the edge strips: they
                 # read no ghost line and may run while the halos travel
                 nstrips = max(s for (s, *_r) in whole) + 1
@@ -192,6 +194,7 @@ def test_sweep_plan_random_geometries(csim):
         inner = csim.sweep_plan(nx, ny, T, nbr, slots, 1)
         frame = csim.sweep_plan(nx, ny, T, nbr, slots, 2)
         assert sorted(inner + frame) == sorted(whole), (nx, ny, T, nbr, slots)
+        assert csim.sweep_plan(nx, ny, T, nbr, slots, 3) == frame + inner, (nx, ny, T, nbr, slots)
         for (s, x0, x1, y0, y1) in inner:
             assert nbr[2] < 0 or y0 - T >= 0, (nx, ny, T, nbr, slots, y0)
             assert nbr[3] < 0 or y1 + T <= ny, (nx, ny, T, nbr, slots, y1)

@@ -559,12 +559,15 @@ def test_cpp_dropin_unit_tests():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("env,path", [({}, "nccl"), ({"CSIM_HALO": "peer"}, "peer"), ({"CSIM_GRAPH": "1"}, "nccl"),
+@pytest.mark.parametrize("env,path", [({}, "nccl"), ({"CSIM_HALO": "peer"}, "peer"), ({"CSIM_LOOP": "coupled"}, "nccl"),
+                                      ({"CSIM_GRAPH": "1"}, "nccl"), ({"CSIM_LOOP": "coupled", "CSIM_HALO": "peer"}, "peer"),
                                       ({"CSIM_HALO": "peer", "CSIM_GRAPH": "1"}, "peer")])
 def test_multi_process_parity_under_torchrun(env, path):
-    """One PROCESS per GPU under torchrun (how bench.py runs): the default NCCL halo path and the peer-store
-    path (CSIM_HALO=peer), which maps the neighbours' tiles with CUDA IPC here — the threaded test above
-    cannot exercise that — and both with the block loop replayed as a CUDA graph."""
+    """One PROCESS per GPU under torchrun (how bench.py runs): the split block loop (frame and interior as two
+    launches on two streams; the default) with the NCCL halo path and with the peer-store path
+    (CSIM_HALO=peer: tiles mapped with CUDA IPC, which the threaded test above cannot exercise), eager and
+    replayed as a CUDA graph, and the coupled loop (CSIM_LOOP=coupled: one sweep launch per block, flags between
+    the sweep and the exchange stream) on both halo paths."""
     import os
     import subprocess
     import sys
