@@ -247,12 +247,13 @@ int csim_comm_allreduce_max(csim_ctx* ctx, double* inout, int n);
  * over NVLink, and unpacked by a kernel; all on the context stream. */
 int csim_halo_exchange(csim_field* f, const csim_decomp* dec);
 
-/* Which halo path csim_run_steps used last on this context: "none" (no neighbours yet), "peer" (the
- * T-line bands are stored straight into the neighbours' ghost lines over NVLink by single-warp CTAs that
- * co-reside with the interior sweep, one flag per neighbour; tiles mapped with CUDA IPC between processes,
- * peer access inside one) or "nccl" (pack kernel, grouped ncclSend/ncclRecv, unpack kernel: CSIM_HALO=nccl,
- * or peers that cannot be mapped).  The peer path is set up on first use — collectively: every rank's
- * first csim_run_steps with a given pair of tiles must be the same call. */
+/* Which halo path csim_run_steps used last on this context: "none" (no neighbours yet), "nccl" (the default:
+ * T-line bands packed by a kernel, one grouped ncclSend/ncclRecv per block, unpack kernel) or "peer"
+ * (CSIM_HALO=peer: the bands are stored straight into the neighbours' ghost lines over NVLink by single-warp
+ * CTAs that co-reside with the interior sweep, one flag per neighbour; tiles mapped with CUDA IPC between
+ * processes, peer access inside one; falls back to "nccl" when a peer cannot be mapped).  The peer path is
+ * set up on first use — collectively: every rank's first csim_run_steps with a given pair of tiles must be
+ * the same call.  Measurements of both: profiles/r02_multigpu.md. */
 const char* csim_halo_path(const csim_ctx* ctx);
 
 /* One region of the wide (T-line, 8-neighbour) exchange csim_run_steps performs per T-step block:
@@ -287,7 +288,11 @@ int csim_sweep_plan(int nx, int ny, int T, const int nbr[4], int resident_warps,
  * communicator and the tile has neighbours), then the fused step.  Equivalent to calling
  * csim_halo_exchange + csim_step_fused(…,1) nsteps times; the library is free to overlap the
  * exchange with the interior update and to block several steps per sweep where that leaves the
- * fields bit-identical. */
+ * fields bit-identical.  Multi-rank runs advance in blocks of T steps (csim_steps_per_sweep): T ghost lines
+ * from all eight neighbours before a block, the sweep split into the work items that read ghost lines (frame)
+ * and the others (interior), the exchange of the next block travelling while the interior items run.
+ * Environment: CSIM_LOOP=coupled runs frame and interior items as one launch coupled to the exchange stream by
+ * device flags; CSIM_GRAPH=1 replays the (split) block loop as a CUDA graph; CSIM_HALO=peer, see csim_halo_path. */
 int csim_run_steps(csim_field* u, csim_field* tmp, const csim_step_params* p,
                    const csim_decomp* dec, int nsteps);
 
