@@ -199,14 +199,15 @@ static int wide_exchange(csim_field* f, const csim_decomp* dec, int T, cudaStrea
     return CSIM_OK;
 }
 
-// ---- peer-memory exchange: the bands go straight into the neighbours' ghost lines -------------------
+// ---- peer-memory exchange (CSIM_HALO=peer): the bands go straight into the neighbours' ghost lines ----
 // Why these kernels are "light".  The interior sweep holds 3 CTAs x 128 threads x 168 registers = 64 512 of
-// an SM's 65 536 registers for its whole duration, and with 320-row chunks a CTA lives ~250 us.  Any
-// helper kernel that needs more than the 1 024 registers left over has to wait for interior CTAs to exit
-// — NCCL's send/recv kernel (one fat CTA) in practice until the TAIL of the interior sweep: measured 770 us
-// per exchange at 16384^2 per GPU, on the frame → exchange → frame chain that bounds the block time
-// (profiles/r02_multigpu.md).  A CTA of ONE warp with at most 32 registers per thread is exactly 1 024
-// registers, so these kernels start at once beside a full interior sweep.
+// an SM's 65 536 registers for its whole duration, and with 320-row chunks a CTA lives ~250 us.  A helper
+// kernel that needs more than the 1 024 registers left over has to wait for interior CTAs to exit; a CTA of
+// ONE warp with at most 32 registers per thread is exactly 1 024 registers and can start beside a full sweep.
+// What was measured (profiles/r02_multigpu.md): on 2 GPUs at 8192^2 per GPU this path beats the NCCL path
+// (1.905e12 against 1.845e12); its own store kernel takes 34 us there but 497 us at 16384^2 per GPU, where a
+// column band spans 2.1 GB of strided rows, and on 8 GPUs (five neighbours, 1.6 MB per exchange) the exchange no
+// longer fits behind the interior sweep and the path collapses — which is why NCCL is the default.
 struct PushRegion {
     int x0, y0, w, h;     // source region in this rank's tile (interior coordinates)
     double* dst;          // neighbour's cell that receives the region's first cell (mapped pointer)

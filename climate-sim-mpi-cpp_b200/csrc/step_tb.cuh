@@ -1,6 +1,9 @@
-// step_tb.cuh — the hot kernel: fused diffusion+advection, T time steps per sweep over HBM.
+// step_tb.cuh — the blocked sweep: fused diffusion+advection, T time steps per pass over HBM.
+// Holds the row routines, the work-item map and the register-only kernel k_step_tb; the default kernel
+// k_step_tbs (step_tbs.cuh) shares all of it and differs only in how the level-0 rows reach the warp
+// (TMA bulk copies into a shared-memory ring instead of register loads), which buys a fourth time level.
 //
-// Design (DESIGN.md §kernels): one WARP owns a strip of 128 columns (4 cells per lane, one 256-bit
+// Design (DESIGN.md §4.1): one WARP owns a strip of 128 columns (4 cells per lane, one 256-bit
 // load per lane per row) and streams down a chunk of rows.  For every time level k < T the warp
 // keeps the two most recent rows of that level in registers; when row r of level 0 arrives from
 // HBM it produces row r-1 of level 1, from that row r-2 of level 2, … and finally stores row r-T of
@@ -18,7 +21,12 @@
 //   - cells on the first/last interior line of a physical side read `value` (Dirichlet) or their
 //     own value (Neumann mirror) instead of the neighbour.
 // These fix-ups run only in the two edge strips and in the first/last row of the tile; interior
-// level-rows take a branch-free fast path.
+// level-rows take a branch-free fast path, and interior rows of strips that merely touch a frozen-ghost
+// or neighbour side take the fast path plus a per-cell keep/advance select (TICK_XMASK).
+//
+// MODE_DIV (a spacing that is not a power of two) keeps the reference's divisions; the divisors are
+// constants of a run, so each quotient is formed from the reciprocal and proved equal to the IEEE quotient
+// (div_by_const_try, step_math.cuh), and a level-row with an unproved quotient is redone with __ddiv_rn.
 //
 // Arithmetic: tb_update issues exactly the reference's operations in the reference's order with
 // non-contractible round-to-nearest intrinsics (see step_math.cuh); MODE_UNIT drops the four
