@@ -21,7 +21,7 @@ def _same(a, b):
     return _bits(a) == _bits(b) or (a != a and b != b)
 
 
-def test_exp_table_is_the_generated_one(csim):
+def test_exp_table_is_the_generated_one(csim, tmp_path):
     """exp_table.inc is what tools/gen_exp_table.py derives from 2^(k/128) with 80-digit arithmetic."""
     import os
     import re
@@ -30,8 +30,10 @@ def test_exp_table_is_the_generated_one(csim):
     from conftest import ROOT
     inc = os.path.join(ROOT, "climate-sim-mpi-cpp_b200", "csrc", "exp_table.inc")
     before = open(inc).read()
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_exp_table.py")], check=True, capture_output=True)
-    assert open(inc).read() == before
+    fresh = str(tmp_path / "exp_table.inc")  # not written in place: the library's build must not look stale
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_exp_table.py"), fresh], check=True,
+                   capture_output=True)
+    assert open(fresh).read() == before
     words = re.findall(r"0x([0-9a-f]{16})ull", before)
     assert len(words) == 256 and words[0] == "0" * 16 and words[1] == "3ff0000000000000"
 
