@@ -185,7 +185,16 @@ def run_reference(args):
               f"bench step, loop time only (main.cpp:89-123 timing region without NetCDF writes); reference compute "
               f"objects, -O2, no MPI launcher (MPI not installed)")
     cfg = base_config(args, dims_for(args.gpus), inner)
-    cfg["workload"] += "; reference arm: ONE tile on the host cores"
+    if args.gpus > 1:  # at N = 1 the two arms run the very same grid
+        cfg["workload"] += "; reference arm: ONE tile on the host cores"
+    # the keys our arm adds to `config`, with this arm's values (same key set in both lines)
+    field_mib = ((tile + 2) * (tile + 2) * 8) >> 20
+    cfg.update({
+        "halo_exchange": f"in-process copies between {used} emulated ranks (threads) following src/halo.cpp:28-43",
+        "arithmetic": "full, 15 FP64 ops per cell in the reference's order, no FMA (g++ -O2 -ffp-contract=off, no -march)",
+        "l2_policy": f"host arm: two {field_mib} MiB fields in host memory, no cache flush between steps",
+        "e2e_workload": "host-resident fields: nothing to copy, e2e = value",
+        "numa_node_of_pinned_buffers": None})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
