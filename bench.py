@@ -117,6 +117,49 @@ def dims_for(n):
     return (n // b, b)
 
 
+FP64_LANES_PER_SM_PER_CLK = 64  # B200: one FP64 instruction per lane slot, 64 slots per SM and clock
+
+
+def fp64_ops_per_cell(vx, vy, dropped):
+    """FP64 instructions one cell update of the blocked sweep issues with unit spacing (csrc/step_tb.cuh,
+    tb_update): 7 for diffusion (two FMA+add line sums, their sum, times dt*D, plus c); per velocity component
+    that is not dropped a difference and a product; one add when both are present; times -dt and the final add."""
+    nx_term = not (dropped and vx == 0.0)
+    ny_term = not (dropped and vy == 0.0)
+    n = 7 + 2 * nx_term + 2 * ny_term
+    if nx_term and ny_term:
+        n += 1
+    if nx_term or ny_term:
+        n += 2
+    return n
+
+
+def computed_over_useful(csim, nx, ny, T, nbr):
+    """Cell updates the sweep computes per cell update it stores, from the library's own host-side plan
+    (csim_sweep_plan): a work item of h rows runs ticks over h + 2T rows (rounded up to two ticks = 4 rows) of
+    all 128 columns of its strip, for every one of the T levels; 120 columns and h rows of level T are stored."""
+    items = csim.sweep_plan(nx, ny, T, tuple(int(v) for v in nbr))
+    rows = sum(4 * ((y1 - y0 + 2 * T + 3) // 4) for (_, _, _, y0, y1) in items)
+    return rows * 128.0 / (float(nx) * float(ny))
+
+
+def fp64_pipe_report(rate_per_gpu, ops, factor, n_sm, sm_mhz, sm_max_mhz):
+    """Share of the FP64 pipe's issue slots the sweep fills: lane-operations per second (cell updates/s x
+    operations per update x re-computation factor) over SMs x 64 lanes x SM clock.  Against the clock sampled
+    during the timed region (what the board ran at under its power cap) and against the maximum clock."""
+    lane_ops = rate_per_gpu * ops * factor
+    out = {"ops_per_cell_update": ops, "computed_over_useful_cells": factor, "lane_ops_per_s": lane_ops,
+           "lanes_per_sm_per_clk": FP64_LANES_PER_SM_PER_CLK, "sms": n_sm, "sm_mhz_sampled": sm_mhz,
+           "frac_at_sampled_clock": None, "frac_at_max_clock": None,
+           "note": "share of the FP64 pipe's issue slots (SMs x 64 lanes x clock) filled by the sweep's FP64 "
+                   "instructions, re-computed halo cells included: the kernel's other ceiling beside HBM"}
+    if sm_mhz:
+        out["frac_at_sampled_clock"] = lane_ops / (n_sm * FP64_LANES_PER_SM_PER_CLK * sm_mhz * 1e6)
+    if sm_max_mhz:
+        out["frac_at_max_clock"] = lane_ops / (n_sm * FP64_LANES_PER_SM_PER_CLK * sm_max_mhz * 1e6)
+    return out
+
+
 def workload_name(tile, dims):
     return (f"{tile}x{tile} per GPU, Gaussian hotspot, diffusion+advection, periodic BCs, "
             f"decomp {{{dims[0]},{dims[1]}}} (global {tile * dims[0]}x{tile * dims[1]})")
@@ -615,6 +658,21 @@ def run_ours(args):
                         "kernel on this tile from the committed ncu capture named in traffic_source (a one-GPU figure: "
                         "counters cannot be read outside a profiler); dram_frac_of_peak = traffic / live launch time / peak"}
 
+    # the kernel's second ceiling: FP64 issue slots (unit spacing only; the division modes issue far more)
+    fp64_general = None
+    try:
+        if (args.dx, args.dy) == (1.0, 1.0) and csim.steps_per_sweep() >= 2:
+            n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            factor = computed_over_useful(csim, dec.nx_local, dec.ny_local, csim.steps_per_sweep(), params.nbr)
+            roofline["fp64_pipe"] = fp64_pipe_report(
+                value / world, fp64_ops_per_cell(PHYS["vx"], PHYS["vy"], dropped), factor, n_sm,
+                clocks.get("sm_mhz"), clocks.get("sm_max_mhz"))
+            fp64_general = fp64_pipe_report(
+                gen_value / world, fp64_ops_per_cell(PHYS_ALL_TERMS["vx"], PHYS_ALL_TERMS["vy"], False), factor, n_sm,
+                clocks_gen.get("sm_mhz"), clocks_gen.get("sm_max_mhz"))
+    except Exception as exc:  # noqa: BLE001 - a report, never a reason to lose the line
+        roofline["fp64_pipe"] = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 64)
@@ -652,7 +710,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "halo": halo, "shared_file": shared_file,
             "all_terms": {"value": gen_value, "unit": "cell-updates/s", "vx": PHYS_ALL_TERMS["vx"],
                           "vy": PHYS_ALL_TERMS["vy"], "steps": gen_steps, "ms_per_step": ms_gen / gen_steps,
-                          "clocks": clocks_gen,
+                          "clocks": clocks_gen, "fp64_pipe": fp64_general,
                           "note": "same windows with both velocity components non-zero (14 FP64 ops per cell): the "
                                   "rate of a run whose velocity has no exact zero component"},
             "gpu_launches": launches, "clocks": clocks,
