@@ -1,4 +1,4 @@
-"""Host-side logic of the N>1 path on CPU: world_size 2 and 4 over torch.distributed/gloo.
+"""Host-side logic of the N>1 path on CPU: world_size 2, 4 and 8 over torch.distributed/gloo.
 
 What runs here is the product's own decomposition (csim_decomp_init) and wide-exchange plan
 (csim_wide_exchange_plan — the same table halo.cu feeds to its pack/NCCL/unpack sequence), with gloo
@@ -84,7 +84,9 @@ def _worker(rank, world, port, nxg, nyg, T, q):
         q.put((rank, False, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,nxg,nyg,T", [(2, 37, 20, 3), (2, 64, 48, 1), (4, 45, 38, 3), (4, 41, 33, 2)])
+# T = 4 is the blocking depth the library runs by default; {4,2} is the 8-GPU decomposition of the scaling runs
+@pytest.mark.parametrize("world,nxg,nyg,T", [(2, 37, 20, 3), (2, 64, 48, 1), (4, 45, 38, 3), (4, 41, 33, 2),
+                                             (2, 50, 31, 4), (4, 53, 47, 4), (8, 83, 41, 4)])
 def test_wide_exchange_plan_over_gloo(world, nxg, nyg, T):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
